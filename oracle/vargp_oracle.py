@@ -1,0 +1,332 @@
+"""CPU oracle for the VAR-GP ELBO hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  Nothing under ``vargp_b200/`` does.
+
+What it is: a plain-PyTorch, CPU, functional restatement of the reference algorithm, op for op
+(including the reference's wasteful parts: the ``B x B`` Gram that is built only for its diagonal,
+the ``t+2`` nested Choleskys, the ``n_v``-fold redundant prior Cholesky), so that
+  (a) it can be timed as "the reference's own CPU implementation" of the path, and
+  (b) it is the arbiter for parity (run it in fp64 for the arbiter, fp32 for the like-for-like check).
+All noise is passed in explicitly (``noise`` dict) instead of being drawn from the global RNG.
+
+Pinning: the reference ships no tests / golden vectors ("parity unpinned" there).
+This oracle is therefore pinned against the *live reference* executed in the build container:
+``tests/golden/make_golden.py`` imports ``/root/reference/var_gp`` with patched RNG, runs the seeded
+cases, and writes ``tests/golden/*.pt``; ``tests/test_oracle_golden.py`` checks this file against those
+fixtures on every CPU test run.
+
+Reference citations are ``file:line`` relative to ``/root/reference``.
+"""
+import math
+
+import torch
+
+JITTER = 1e-4  # var_gp/gp_utils.py:5 (default eps of `cholesky`)
+
+
+# ----------------------------------------------------------------------------------------------
+# var_gp/kernels.py
+# ----------------------------------------------------------------------------------------------
+def rbf_compute(theta, x, y=None):
+  """ARD-RBF Gram, var_gp/kernels.py:24-56.  theta (H, D+1); x (..., M, D); y (..., N, D) or None.
+
+  Returns (H, ..., M, N).  Follows the reference's three-Gram construction (xx, yy, xy and the two
+  diagonals) so rounding matches; `y is None` re-uses xx for all three (diagonal is exactly gamma^2).
+  """
+  n_h = theta.size(0)
+  th = theta.reshape(n_h, 1, *([1] * (x.dim() - 2)), theta.size(-1))
+  ell = th[..., :-1].exp()
+  amp2 = (2. * th[..., -1:]).exp()
+
+  xs = x.unsqueeze(0) / ell
+  g_xx = xs @ xs.transpose(-1, -2)
+  if y is None:
+    g_yy = g_xy = g_xx
+  else:
+    ys = y.unsqueeze(0) / ell
+    g_yy = ys @ ys.transpose(-1, -2)
+    g_xy = xs @ ys.transpose(-1, -2)
+  d2 = -2. * g_xy + g_xx.diagonal(dim1=-2, dim2=-1).unsqueeze(-1) \
+       + g_yy.diagonal(dim1=-2, dim2=-1).unsqueeze(-2)
+  return amp2 * (-.5 * d2).exp()
+
+
+def rbf_diag(theta):
+  """var_gp/kernels.py:58-60 -> (H, 1, 1)."""
+  return (2. * theta[..., -1:]).exp().unsqueeze(-2)
+
+
+def sample_hypers(log_mean, log_logvar, eps_theta):
+  """var_gp/kernels.py:62-68 with the N(0,1) draw made explicit: eps_theta (H, D+1)."""
+  return log_mean + log_logvar.exp().sqrt() * eps_theta
+
+
+def kl_hypers(log_mean, log_logvar, prior_log_mean, prior_log_logvar):
+  """var_gp/kernels.py:70-77: sum over D+1 of KL(N(m_q, s_q^2) || N(m_p, s_p^2))
+  (closed form of torch.distributions.kl._kl_normal_normal)."""
+  s_q = log_logvar.exp().sqrt()
+  s_p = prior_log_logvar.exp().sqrt()
+  var_ratio = (s_q / s_p).pow(2)
+  t1 = ((log_mean - prior_log_mean) / s_p).pow(2)
+  return (0.5 * (var_ratio + t1 - 1. - var_ratio.log())).sum(0)
+
+
+# ----------------------------------------------------------------------------------------------
+# var_gp/gp_utils.py
+# ----------------------------------------------------------------------------------------------
+def chol_jitter(mat, eps=JITTER):
+  """var_gp/gp_utils.py:5-11."""
+  eye = torch.eye(mat.size(-1), dtype=mat.dtype)
+  return torch.linalg.cholesky(mat + eps * eye)
+
+
+def llt(L):
+  """var_gp/gp_utils.py:14-19."""
+  return L @ L.transpose(-1, -2)
+
+
+def vec2tril(vec, m=None):
+  """var_gp/gp_utils.py:22-49: packed row-major lower triangle -> matrix, softplus on the diagonal."""
+  if m is None:
+    m = int((math.sqrt(8. * vec.size(-1) + 1.) - 1.) / 2.)
+  rows, cols = torch.tril_indices(m, m)
+  out = torch.zeros(*vec.shape[:-1], m, m, dtype=vec.dtype)
+  out[..., rows, cols] = vec
+  on_diag = torch.eye(m, dtype=torch.bool)
+  return torch.where(on_diag, torch.nn.functional.softplus(out), out)
+
+
+def mat2trilvec(mat):
+  """var_gp/gp_utils.py:52-65."""
+  rows, cols = torch.tril_indices(mat.size(-1), mat.size(-1))
+  return mat[..., rows, cols]
+
+
+def _lsolve(L, rhs):
+  """left, lower, no-transpose triangular solve (torch.triangular_solve(rhs, L, upper=False))."""
+  shape = torch.broadcast_shapes(L.shape[:-2], rhs.shape[:-2])
+  return torch.linalg.solve_triangular(L.expand(*shape, *L.shape[-2:]),
+                                       rhs.expand(*shape, *rhs.shape[-2:]), upper=False)
+
+
+def _atb(a, b):
+  """einsum('...ij,...ik->...jk')."""
+  return a.transpose(-1, -2) @ b
+
+
+def gp_cond(u, Kzz, Kzx, Kxx, Lz=None, Lz_Kzx=None):
+  """var_gp/gp_utils.py:68-98."""
+  if Lz is None:
+    Lz = chol_jitter(Kzz)
+  Lz_u = _lsolve(Lz, u)
+  if Lz_Kzx is None:
+    Lz_Kzx = _lsolve(Lz, Kzx)
+  mu = _atb(Lz_Kzx, Lz_u)
+  cov = Kxx - _atb(Lz_Kzx, Lz_Kzx)
+  return mu, cov
+
+
+def linear_joint(m, S, Kzx, Kzz, V, b, cache=None):
+  """var_gp/gp_utils.py:101-147."""
+  Lz = chol_jitter(Kzz)
+  Lz_m = _lsolve(Lz, m)
+  Lz_Kzx = _lsolve(Lz, Kzx)
+  Am = _atb(Lz_Kzx, Lz_m)
+  Lz_S = _lsolve(Lz, S)
+  AS = _atb(Lz_Kzx, Lz_S)
+  SAt = AS.transpose(-1, -2)
+  Lz_SAt = _lsolve(Lz, SAt)
+  ASAt = _atb(Lz_SAt, Lz_Kzx)
+  mu = torch.cat([m, Am + b], dim=-2)
+  cov = torch.cat([torch.cat([S, SAt], dim=-1),
+                   torch.cat([AS, V + ASAt], dim=-1)], dim=-2)
+  if isinstance(cache, dict):
+    cache.update(Lz_Kzx=Lz_Kzx, Lz=Lz)
+  return mu, cov
+
+
+def linear_marginal_diag(m, S, Kzz, Kzx, Kxx_diag, cache=None):
+  """var_gp/gp_utils.py:150-191."""
+  Lz = chol_jitter(Kzz)
+  Lz_m = _lsolve(Lz, m)
+  Lz_Kzx = _lsolve(Lz, Kzx)
+  mu = _atb(Lz_Kzx, Lz_m).squeeze(-1)
+  d1 = Lz_Kzx.pow(2).sum(dim=-2)
+  Lz_LS = _lsolve(Lz, chol_jitter(S))
+  d2 = _atb(Lz_LS, Lz_Kzx).pow(2).sum(dim=-2)
+  var = Kxx_diag - d1 + d2
+  if isinstance(cache, dict):
+    cache.update(Lz=Lz, Lz_Kzx=Lz_Kzx)
+  return mu, var
+
+
+# ----------------------------------------------------------------------------------------------
+# var_gp/likelihoods.py (MulticlassSoftmax)
+# ----------------------------------------------------------------------------------------------
+def softmax_samples(mu, var, eps_f):
+  """var_gp/likelihoods.py:13-31 with explicit eps_f (H, F, C, B)."""
+  f = mu.unsqueeze(1) + var.sqrt().unsqueeze(1) * eps_f
+  return torch.log_softmax(f, dim=-2)
+
+
+def softmax_nll(mu, var, y, eps_f):
+  """var_gp/likelihoods.py:33-47: sum_b mean_h mean_f -log p(y_b)."""
+  logp = softmax_samples(mu, var, eps_f)                       # (H, F, C, B)
+  idx = y.view(1, 1, 1, -1).expand(logp.size(0), logp.size(1), 1, -1)
+  picked = logp.gather(2, idx).squeeze(2)                      # (H, F, B)
+  return -(picked.mean(1).mean(0)).sum(0)
+
+
+def softmax_predict(mu, var, eps_f):
+  """var_gp/likelihoods.py:49-63 -> (B, C)."""
+  logp = softmax_samples(mu, var, eps_f)
+  flat = logp.reshape(-1, *mu.shape[-2:])
+  return (flat.logsumexp(dim=0).exp() / flat.size(0)).T
+
+
+# ----------------------------------------------------------------------------------------------
+# torch.distributions pieces the reference leans on (vargp.py:137-138, 182-190)
+# ----------------------------------------------------------------------------------------------
+def mvn_kl_tril(mu_q, L_q, mu_p, L_p):
+  """KL(N(mu_q, L_q L_q^T) || N(mu_p, L_p L_p^T)); restates
+  torch.distributions.kl._kl_multivariatenormal_multivariatenormal (torch 2.11)."""
+  n = mu_q.size(-1)
+  half_logdet = L_p.diagonal(dim1=-2, dim2=-1).log().sum(-1) - L_q.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+  tr = _lsolve(L_p, L_q).pow(2).sum((-2, -1))
+  diff = (mu_p - mu_q).unsqueeze(-1)
+  maha = _lsolve(L_p, diff).pow(2).sum((-2, -1))
+  return half_logdet + 0.5 * (tr + maha - n)
+
+
+# ----------------------------------------------------------------------------------------------
+# var_gp/vargp.py
+# ----------------------------------------------------------------------------------------------
+def compute_q(theta, prev, z, u_mean, u_tril_vec, cache=None):
+  """var_gp/vargp.py:35-88.  `prev` = list of dict(z, u_mean, u_tril) with u_tril already unpacked."""
+  H = theta.size(0)
+  z_lt = prev[0]['z']
+  mu_lt = prev[0]['u_mean'].unsqueeze(0).expand(H, -1, -1, -1)
+  S_lt = llt(prev[0]['u_tril']).unsqueeze(0).expand(H, -1, -1, -1)
+  for p in prev[1:]:
+    Kzx = rbf_compute(theta, z_lt, p['z'])
+    Kzz = rbf_compute(theta, z_lt)
+    V = llt(p['u_tril']).unsqueeze(0).expand(H, -1, -1, -1)
+    b = p['u_mean'].unsqueeze(0).expand(H, -1, -1, -1)
+    mu_lt, S_lt = linear_joint(mu_lt, S_lt, Kzx, Kzz, V, b)
+    z_lt = torch.cat([z_lt, p['z']], dim=-2)
+  Kzx = rbf_compute(theta, z_lt, z)
+  Kzz = rbf_compute(theta, z_lt)
+  V = llt(vec2tril(u_tril_vec)).unsqueeze(0).expand(H, -1, -1, -1)
+  b = u_mean.unsqueeze(0).expand(H, -1, -1, -1)
+  c = dict()
+  mu_leq, S_leq = linear_joint(mu_lt, S_lt, Kzx, Kzz, V, b, cache=c)
+  z_leq = torch.cat([z_lt, z], dim=-2)
+  if isinstance(cache, dict):
+    cache['Lz_lt'] = c['Lz']
+    cache['Lz_lt_Kz_lt_z_t'] = c['Lz_Kzx']
+  return mu_lt, S_lt, mu_leq, S_leq, z_leq
+
+
+def compute_pf_diag(theta, x, mu_leq, S_leq, z_leq, cache=None):
+  """var_gp/vargp.py:90-113."""
+  xf = x.unsqueeze(0).expand(z_leq.size(0), -1, -1)
+  Kzz = rbf_compute(theta, z_leq)
+  Kzx = rbf_compute(theta, z_leq, xf)
+  return linear_marginal_diag(mu_leq, S_leq, Kzz, Kzx, rbf_diag(theta), cache=cache)
+
+
+def forward(params, prev, x, noise, n_v, ep_var_mean=True, want_loss_cache=False, map_est=False):
+  """var_gp/vargp.py:115-175.
+
+  params: dict(z (C,M,D), u_mean (C,M,1), u_tril_vec (C,M(M+1)/2), log_mean, log_logvar)
+  prev:   list of dict(z, u_mean, u_tril_vec) for tasks < t (constants)
+  noise:  dict(eps_theta (H,D+1), eps_u (n_v,H,C,Q) if t>0 and want_loss_cache, eps_f (H,F,C,B))
+  Returns f_mean, f_var (H,C,B) and the loss cache (or None).
+  """
+  z, u_mean, u_tril_vec = params['z'], params['u_mean'], params['u_tril_vec']
+  M = z.size(-2)
+  if map_est:
+    theta = params['log_mean'].unsqueeze(0)
+  else:
+    theta = sample_hypers(params['log_mean'], params['log_logvar'], noise['eps_theta'])
+  prevp = [dict(z=p['z'], u_mean=p['u_mean'], u_tril=vec2tril(p['u_tril_vec'])) for p in prev]
+  lc = None
+  if prevp:
+    cq = dict()
+    mu_lt, S_lt, mu_leq, S_leq, z_leq = compute_q(theta, prevp, z, u_mean, u_tril_vec, cache=cq)
+    f_mean, f_var = compute_pf_diag(theta, x, mu_leq, S_leq, z_leq)
+    if want_loss_cache:
+      # MultivariateNormal(mu, covariance_matrix=S).rsample([n_v]): no-jitter Cholesky (vargp.py:137-138)
+      L_S = torch.linalg.cholesky(S_lt)
+      u_lt = mu_lt.squeeze(-1).unsqueeze(0) + (L_S.unsqueeze(0) @ noise['eps_u'].unsqueeze(-1)).squeeze(-1)
+      u_lt = u_lt.unsqueeze(-1)                                     # (n_v, H, C, Q, 1)
+      Lz = cq['Lz_lt'].unsqueeze(0)
+      Lz_Kzx = cq['Lz_lt_Kz_lt_z_t'].unsqueeze(0).expand(n_v, *([-1] * (Lz.dim() - 1)))
+      Kzz_t = rbf_compute(theta, z).unsqueeze(0)
+      prior_mu, prior_cov = gp_cond(u_lt, None, None, Kzz_t, Lz=Lz, Lz_Kzx=Lz_Kzx)
+      var_mu = prior_mu * float(ep_var_mean) + u_mean.unsqueeze(0).unsqueeze(0)
+      var_L = vec2tril(u_tril_vec, M).unsqueeze(0).unsqueeze(0)
+      lc = dict(var_mu_t=var_mu.squeeze(-1), var_L_cov_t=var_L,
+                prior_mu_t=prior_mu.squeeze(-1), prior_L_cov_t=chol_jitter(prior_cov))
+  else:
+    cpf = dict()
+    L_u = vec2tril(u_tril_vec, M)
+    f_mean, f_var = compute_pf_diag(theta, x, u_mean, llt(L_u), z, cache=cpf)
+    if want_loss_cache:
+      mu_t = u_mean.squeeze(-1).unsqueeze(0).unsqueeze(0)
+      lc = dict(var_mu_t=mu_t, var_L_cov_t=L_u.unsqueeze(0).unsqueeze(0),
+                prior_mu_t=torch.zeros_like(mu_t), prior_L_cov_t=cpf['Lz'].unsqueeze(0))
+  return f_mean, f_var, lc
+
+
+def elbo_terms(params, prev, x, y, noise, n_v, ep_var_mean=True, map_est=False):
+  """var_gp/vargp.py:177-194 -> (kl_hypers, kl_u, nll)."""
+  f_mean, f_var, lc = forward(params, prev, x, noise, n_v, ep_var_mean, want_loss_cache=True, map_est=map_est)
+  nll = softmax_nll(f_mean, f_var, y, noise['eps_f'])
+  kl = mvn_kl_tril(lc['var_mu_t'], lc['var_L_cov_t'], lc['prior_mu_t'], lc['prior_L_cov_t'])
+  kl_u = kl.sum(-1).mean(0).mean(0)
+  if map_est:
+    kl_h = torch.zeros((), dtype=f_mean.dtype)
+  else:
+    kl_h = kl_hypers(params['log_mean'], params['log_logvar'],
+                     params['prior_log_mean'], params['prior_log_logvar'])
+  return kl_h, kl_u, nll
+
+
+def predict(params, prev, x, noise, n_v, map_est=False):
+  """var_gp/vargp.py:196-198 -> probs (B, C)."""
+  f_mean, f_var, _ = forward(params, prev, x, noise, n_v, want_loss_cache=False, map_est=map_est)
+  return softmax_predict(f_mean, f_var, noise['eps_f'])
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers shared by tests / bench: seeded synthetic cases
+# ----------------------------------------------------------------------------------------------
+def make_case(C, D, M, t, B, H=3, F=10, seed=0, sigma=10., dtype=torch.float32, with_eps_u=True,
+              sparse=False, n_v=None):
+  """Seed-pinned synthetic problem.  Everything is drawn in fp64 from one CPU generator and cast, so
+  fp32 and fp64 cases see the same numbers.  H = number of hyper samples actually drawn (1 under
+  map_est), n_v = n_var_samples of the model (defaults to H).  Returns (params, prev, x, y, noise)."""
+  n_v = H if n_v is None else n_v
+  g = torch.Generator().manual_seed(seed)
+  U = lambda *s: torch.rand(*s, generator=g, dtype=torch.float64)
+  Nrm = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+  T = M * (M + 1) // 2
+  prev = [dict(z=U(C, M, D).to(dtype), u_mean=(0.5 * Nrm(C, M, 1)).to(dtype),
+               u_tril_vec=(0.1 * Nrm(C, T)).to(dtype)) for _ in range(t)]
+  log_mean = torch.cat([math.log(sigma) + 0.05 * Nrm(D), torch.full((1,), -0.7, dtype=torch.float64)])
+  params = dict(z=U(C, M, D).to(dtype), u_mean=(0.5 * Nrm(C, M, 1)).to(dtype),
+                u_tril_vec=(0.1 * Nrm(C, T)).to(dtype),
+                log_mean=log_mean.to(dtype), log_logvar=(-2. + 0.1 * Nrm(D + 1)).to(dtype),
+                prior_log_mean=(log_mean + 0.1 * Nrm(D + 1)).to(dtype),
+                prior_log_logvar=(-1.5 + 0.1 * Nrm(D + 1)).to(dtype))
+  x = U(B, D)
+  if sparse:
+    x = x * (U(B, D) < 0.19)
+  x = x.to(dtype)
+  y = torch.randint(0, C, (B,), generator=g)
+  noise = dict(eps_theta=Nrm(H, D + 1).to(dtype), eps_f=Nrm(H, F, C, B).to(dtype))
+  if t > 0 and with_eps_u:
+    noise['eps_u'] = Nrm(n_v, H, C, t * M).to(dtype)
+  return params, prev, x, y, noise

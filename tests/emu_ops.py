@@ -1,0 +1,148 @@
+"""Torch emulation of the ``vargp_b200.ops`` kernel interface  --  TEST INFRASTRUCTURE ONLY.
+
+Lets the CPU test-suite (``-m "not gpu"``) exercise the *host schedule* of the hot path
+(``vargp_b200/elbo.py``: which kernel is called on which view with which flags, and the hand-derived
+backward) without a GPU, in fp32 or fp64.  Each method states the contract the CUDA kernel of the same
+name implements; the GPU tests check the kernels against these same contracts.  Never imported by
+``vargp_b200``: the product path fails loudly when the CUDA library is missing.
+"""
+import torch
+
+
+def _tri(x, kind):
+  if kind is None:
+    return x
+  return torch.tril(x) if kind == 'lower' else torch.triu(x)
+
+
+class EmuOps:
+  name = 'emu'
+
+  def scale_rows(self, src, theta, dst, norms):
+    D = src.shape[-1]
+    dst.copy_(src.unsqueeze(0) * torch.exp(-theta[:, :D]).unsqueeze(1))
+    norms.copy_((dst * dst).sum(-1))
+
+  def rbf_gram(self, a, an, b, bn, theta, out, sym):
+    g2 = torch.exp(2. * theta[:, -1]).view(-1, 1, 1, 1)
+    dot = a @ b.transpose(-1, -2)
+    val = g2 * torch.exp(dot - 0.5 * an.unsqueeze(-1) - 0.5 * bn.unsqueeze(-2))
+    if sym:
+      eye = torch.eye(a.shape[-2], dtype=torch.bool, device=a.device)
+      val = torch.where(eye, g2.expand_as(val), val)
+    out.copy_(val)
+
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None):
+    prod = alpha * (_tri(A, a_tri) @ _tri(B, b_tri))
+    if c_tri is not None:
+      prod = _tri(prod, c_tri)
+    if beta == 0.:
+      C.copy_(prod)
+    else:
+      C.copy_(prod + beta * C)
+
+  def chol(self, K, L, jitter, info):
+    eye = torch.eye(K.shape[-1], dtype=K.dtype, device=K.device)
+    Lc, inf = torch.linalg.cholesky_ex(K + jitter * eye)
+    L.copy_(Lc)
+    info.copy_(inf.reshape(-1))
+
+  def trtri(self, L, W):
+    eye = torch.eye(L.shape[-1], dtype=L.dtype, device=L.device).expand_as(L)
+    W.copy_(torch.linalg.solve_triangular(L, eye, upper=False))
+
+  def kl_fwd(self, W, T, nu, Lu_t, M, kl):
+    H = W.shape[0]
+    P = W.shape[-1]
+    wd = W.diagonal(dim1=-2, dim2=-1)[..., P - M:]
+    val = -wd.log().sum() - H * Lu_t.diagonal(dim1=-2, dim2=-1).log().sum() \
+          + 0.5 * ((T[:, :, -1] ** 2).sum() + (nu[..., P - M:] ** 2).sum() - M * W.shape[0] * W.shape[1])
+    kl.add_(val / H)
+
+  def kl_bwd(self, W, T, nu, M, g_kl, Wbar, Tbar, nubar):
+    H = W.shape[0]
+    P = W.shape[-1]
+    s = g_kl / H
+    Tbar[:, :, -1] += s * T[:, :, -1]
+    nubar[..., P - M:] += s * nu[..., P - M:]
+    wd = W.diagonal(dim1=-2, dim2=-1)[..., P - M:]
+    Wbar.diagonal(dim1=-2, dim2=-1)[..., P - M:] -= s / wd
+
+  def kl_bwd_lu(self, Lu_t, g_kl, Lu_bar_t):
+    Lu_bar_t.diagonal(dim1=-2, dim2=-1).sub_(g_kl / Lu_t.diagonal(dim1=-2, dim2=-1))
+
+  def marginal_reduce(self, V, TV, A, nu, theta, jitter, f_mean, f_var):
+    g2 = torch.exp(2. * theta[:, -1]).view(-1, 1, 1)
+    f_mean.copy_((V * nu.unsqueeze(-1)).sum(-2))
+    f_var.copy_(g2 - (V * V).sum(-2) + (TV * TV).sum(-2) + jitter * (A * A).sum(-2))
+
+  def marginal_bwd_prep(self, V, TV, A, nu, g_mean, g_var, theta, jitter, Vbar, theta_bar):
+    gv = g_var.unsqueeze(-2)
+    theta_bar[:, -1] += 2. * torch.exp(2. * theta[:, -1]) * g_var.sum((1, 2))
+    Vbar.copy_(nu.unsqueeze(-1) * g_mean.unsqueeze(-2) - 2. * V * gv)
+    A.mul_(2. * jitter * gv)
+    TV.mul_(2. * gv)
+
+  def sym_phi(self, X):
+    low = torch.tril(X, -1)
+    d = torch.diag_embed(X.diagonal(dim1=-2, dim2=-1))
+    X.copy_(0.5 * (low + low.transpose(-1, -2) + d))
+
+  def rbf_bwd_prep(self, Kbar, K, rsum, csum):
+    Kbar.mul_(K)
+    rsum.copy_(Kbar.sum(-1))
+    if csum is not None:
+      csum.add_(Kbar.sum(-2).sum(1))
+
+  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar):
+    D = zs.shape[-1]
+    r = (r1 + 2. * r2).unsqueeze(-1)
+    zsb = -r * zs + 2. * Gz2
+    acc = -zs * zsb
+    if Gz1 is not None:
+      zsb = zsb + Gz1
+      acc = -zs * zsb - zs * Gz1
+    Z_bar.copy_((zsb * torch.exp(-theta[:, :D]).view(-1, 1, 1, D)).sum(0))
+    theta_bar[:, :D] += acc.sum((1, 2))
+    theta_bar[:, D] += 2. * (r1 + r2).sum((1, 2))
+
+  def rbf_bwd_xside(self, xs, csum, Gx, theta, theta_bar, x_bar):
+    D = xs.shape[-1]
+    theta_bar[:, :D] += (csum.unsqueeze(-1) * xs * xs).sum(1)
+    if x_bar is not None:
+      xsb = -csum.unsqueeze(-1) * xs + Gx.sum(1)
+      x_bar.copy_((xsb * torch.exp(-theta[:, :D]).unsqueeze(1)).sum(0))
+
+  def tril_unpack(self, vec, out):
+    M = out.shape[-1]
+    r, c = torch.tril_indices(M, M)
+    out.zero_()
+    out[..., r, c] = vec
+    d = out.diagonal(dim1=-2, dim2=-1)
+    d.copy_(torch.nn.functional.softplus(d))
+
+  def tril_unpack_bwd(self, Lbar, vec, vec_bar):
+    M = Lbar.shape[-1]
+    r, c = torch.tril_indices(M, M)
+    g = Lbar[..., r, c].clone()
+    on = (r == c)
+    g[..., on] = g[..., on] * torch.sigmoid(vec[..., on])
+    vec_bar.copy_(g)
+
+  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var):
+    H, F, C, B = eps_f.shape
+    sd = f_var.sqrt().unsqueeze(1)
+    f = f_mean.unsqueeze(1) + sd * eps_f
+    logp = torch.log_softmax(f, dim=-2)
+    idx = y.view(1, 1, 1, B).expand(H, F, 1, B)
+    nll.add_(-logp.gather(2, idx).sum() / (H * F))
+    gf = logp.exp()
+    gf.scatter_add_(2, idx, -torch.ones_like(gf[:, :, :1]))
+    gf = gf / (H * F)
+    g_mean.copy_(gf.sum(1))
+    g_var.copy_((gf * eps_f).sum(1) / (2. * sd.squeeze(1)))
+
+  def predict(self, f_mean, f_var, eps_f, probs):
+    H, F, C, B = eps_f.shape
+    f = f_mean.unsqueeze(1) + f_var.sqrt().unsqueeze(1) * eps_f
+    probs.copy_(torch.softmax(f, dim=-2).sum((0, 1)).T / (H * F))

@@ -1,0 +1,205 @@
+"""Fused sparse-variational marginal + KL(u) for VAR-GP, with a hand-derived backward.
+
+This is the host-side schedule of the hot path: it owns no arithmetic.  Every number is produced by a
+kernel of ``libvargp_sm100.so`` reached through ``vargp_b200.ops`` (C-ABI, raw pointers + strides).
+
+Formulation.  For each hyper sample h and class c, with
+Z = [z_0; ...; z_t] (P = (t+1) M rows) and K = K_h(Z, Z) + eps I:
+
+    W   = chol(K)^-1                         one Cholesky + one triangular inverse   (replaces the t+2
+                                             Choleskys of var_gp/vargp.py:61-80,108,155)
+    T_s = W_ss Lu_s ,  nu_s = W_ss m_s       whitened variational factor / mean: the autoregressive joint
+                                             of var_gp/gp_utils.py:101-147 is block-diagonal here
+    V   = W Kzx ,  a = W^T V
+    f_mean_b = nu . V_b
+    f_var_b  = gamma^2 - |V_b|^2 + sum_s |T_s^T V_sb|^2 + eps |a_b|^2        (gp_utils.py:150-191)
+    KL_hc    = -sum_{i in t} log W_ii - sum_i log Lu_t,ii + (|T_t|_F^2 + |nu_t|^2 - M) / 2
+    kl_u     = (1/H) sum_hc KL_hc                                             (vargp.py:182-190)
+
+(the KL line holds for ``ep_var_mean=True``; the block-diagonal ablation goes through
+``vargp_b200.gp_utils``).  All O(P^2 B) and O(P^3) work is expressed as batched GEMMs so it can run on
+the tensor cores; nothing of size B x B is ever formed.
+"""
+import torch
+
+from . import ops as _ops_mod
+
+JITTER = 1e-4   # var_gp/gp_utils.py:5
+
+
+def _ops():
+  return _ops_mod.get_ops()
+
+
+class _Ctx:
+  """Plain container for tensors saved between forward and backward."""
+  pass
+
+
+def _blocks(mat, S, M):
+  """(H, C, P, P) -> view (H, C, S, M, M) of the S diagonal M x M blocks (no copy)."""
+  H, C, P, _ = mat.shape
+  sH, sC, sR, sC2 = mat.stride()
+  return mat.as_strided((H, C, S, M, M), (sH, sC, M * sR + M * sC2, sR, sC2))
+
+
+def _rows(mat, S, M):
+  """(H, C, P, B) -> view (H, C, S, M, B) of the S row blocks."""
+  H, C, P, B = mat.shape
+  sH, sC, sR, sB = mat.stride()
+  return mat.as_strided((H, C, S, M, B), (sH, sC, M * sR, sR, sB))
+
+
+def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
+  """theta (H, D+1); Zcat (C, P, D); x (B, D); m_all (S, C, M); Lu_all (S, C, M, M) lower.
+
+  Returns f_mean, f_var (H, C, B), kl_u (0-d tensor or None) and fills ``ctx`` for the backward.
+  """
+  ops = _ops()
+  H, D1 = theta.shape
+  D = D1 - 1
+  C, P, _ = Zcat.shape
+  B = x.shape[0]
+  S = P // M
+  dev, dt = x.device, x.dtype
+  new = lambda *s: torch.empty(*s, device=dev, dtype=dt)
+
+  # (1) scaled operands and their squared norms                               [kernels.py:41-44,50]
+  zs, zn = new(H, C * P, D), new(H, C * P)
+  xs, xn = new(H, B, D), new(H, B)
+  ops.scale_rows(Zcat.reshape(C * P, D), theta, zs, zn)
+  ops.scale_rows(x, theta, xs, xn)
+  zs4, zn3 = zs.view(H, C, P, D), zn.view(H, C, P)
+
+  # (2) Gram matrices                                                          [kernels.py:45-56]
+  Kzz, Kzx = new(H, C, P, P), new(H, C, P, B)
+  ops.rbf_gram(zs4, zn3, zs4, zn3, theta, Kzz, True)
+  ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False)
+
+  # (3) W = chol(Kzz + eps I)^-1                                               [gp_utils.py:5-11]
+  L, W = new(H, C, P, P), new(H, C, P, P)
+  info = torch.zeros(H * C, device=dev, dtype=torch.int32)
+  ops.chol(Kzz, L, JITTER, info)
+  ops.trtri(L, W)
+
+  # (4) whitened variational parameters (block diagonal)
+  T, nu = new(H, C, S, M, M), new(H, C, P)
+  Wd = _blocks(W, S, M)
+  LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M), broadcast over h
+  ops.gemm(Wd, LuB, T, a_tri='lower', b_tri='lower')
+  mB = m_all.permute(1, 0, 2).unsqueeze(0).unsqueeze(-1)        # (1, C, S, M, 1)
+  ops.gemm(Wd, mB, nu.view(H, C, S, M, 1), a_tri='lower')
+
+  # (5) KL(q(u_t | u_<t) || p(u_t | u_<t))                                     [vargp.py:182-190]
+  kl = None
+  if want_kl:
+    kl = torch.zeros((), device=dev, dtype=dt)
+    ops.kl_fwd(W, T, nu, Lu_all[S - 1], M, kl)
+
+  # (6) predictive marginal                                                    [gp_utils.py:150-191]
+  V, TV, A = new(H, C, P, B), new(H, C, P, B), new(H, C, P, B)
+  ops.gemm(W, Kzx, V, a_tri='lower')
+  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper')
+  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper')
+  f_mean, f_var = new(H, C, B), new(H, C, B)
+  ops.marginal_reduce(V, TV, A, nu, theta, JITTER, f_mean, f_var)
+
+  if ctx is not None:
+    ctx.dims = (H, C, P, B, D, S, M)
+    ctx.saved = dict(theta=theta, zs=zs4, xs=xs, Kzz=Kzz, Kzx=Kzx, W=W, T=T, nu=nu, V=V, TV=TV, A=A,
+                     m_all=m_all, Lu_all=Lu_all)
+  return f_mean, f_var, kl, info, L
+
+
+def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
+  """Adjoint of `marginal_forward`.  g_mean, g_var (H, C, B) or None; g_kl 0-d tensor or None.
+
+  Returns grads (theta (H, D+1), Zcat (C, P, D), x (B, D) or None, m_all (S, C, M), Lu_all (S, C, M, M)).
+  """
+  ops = _ops()
+  H, C, P, B, D, S, M = ctx.dims
+  sv = ctx.saved
+  theta, zs, xs, Kzz, Kzx, W, T, nu = (sv[k] for k in ('theta', 'zs', 'xs', 'Kzz', 'Kzx', 'W', 'T', 'nu'))
+  V, TV, A, m_all, Lu_all = (sv[k] for k in ('V', 'TV', 'A', 'm_all', 'Lu_all'))
+  dev, dt = V.device, V.dtype
+  new = lambda *s: torch.empty(*s, device=dev, dtype=dt)
+  zeros = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+  Wd = _blocks(W, S, M)
+  LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M)
+  mB = m_all.permute(1, 0, 2).unsqueeze(0)                      # (1, C, S, M)
+
+  theta_bar = zeros(H, D + 1)
+  Wbar = zeros(H, C, P, P)
+  Tbar = zeros(H, C, S, M, M)
+  nubar = zeros(H, C, P)
+  Kxbar = None
+  have_data = g_mean is not None or g_var is not None
+  if have_data:
+    if g_mean is None:
+      g_mean = torch.zeros_like(g_var)
+    if g_var is None:
+      g_var = torch.zeros_like(g_mean)
+    g_mean, g_var = g_mean.contiguous(), g_var.contiguous()
+    # Vbar = nu gm^T - 2 V gv ; A <- 2 eps gv A ; TV <- 2 gv TV           (A, TV overwritten in place)
+    # theta_bar[:, D] += 2 gamma^2 sum_cb gv      (direct gamma^2 term of f_var)
+    Vbar = new(H, C, P, B)
+    ops.marginal_bwd_prep(V, TV, A, nu, g_mean, g_var, theta, JITTER, Vbar, theta_bar)
+    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower')
+    ops.gemm(W, A, Vbar, beta=1., a_tri='lower')
+    # Kzx_bar = W^T Vbar
+    Kxbar = new(H, C, P, B)
+    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper')
+    # Wbar = tril(Vbar Kzx^T + V Abar^T)
+    ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower')
+    ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower')
+    # Tbar_s = V_s TVg_s^T ; nubar = V gm
+    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar)
+    ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1))
+  if g_kl is not None:
+    # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block
+    ops.kl_bwd(W, T, nu, M, g_kl, Wbar, Tbar, nubar)
+
+  # whitening adjoint: Wbar_ss += tril(Tbar_s Lu_s^T + nubar_s m_s^T); Lu_bar_s = sum_h W_ss^T Tbar_s ; m_bar_s = sum_h W_ss^T nubar_s
+  Wbd = _blocks(Wbar, S, M)
+  ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., c_tri='lower')
+  ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower')
+  Lubar_h = new(H, C, S, M, M)
+  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower')
+  mbar_h = new(H, C, S, M, 1)
+  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper')
+  Lu_bar = Lubar_h.sum(0).permute(1, 0, 2, 3).contiguous()      # (S, C, M, M)
+  m_bar = mbar_h.sum(0).squeeze(-1).permute(1, 0, 2).contiguous()
+  if g_kl is not None:
+    # d/dLu_t of -sum_i log Lu_t,ii  (mean over h of H identical terms)
+    ops.kl_bwd_lu(Lu_all[S - 1], g_kl, Lu_bar[S - 1])
+
+  # Cholesky-inverse adjoint:  Kbar = -W^T Xi W,  Xi = (Phi(X) + Phi(X)^T)/2,  X = tril(Wbar W^T)
+  X = new(H, C, P, P)
+  ops.gemm(Wbar, W.transpose(-1, -2), X, a_tri='lower', b_tri='upper', c_tri='lower')
+  ops.sym_phi(X)                                                 # in place -> Xi (full symmetric)
+  Y = new(H, C, P, P)
+  ops.gemm(X, W, Y, b_tri='lower')
+  Kzzbar = new(H, C, P, P)
+  ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper')
+
+  # RBF adjoint                                                                 
+  r1, r2 = zeros(H, C, P), new(H, C, P)
+  csum = zeros(H, B)
+  ops.rbf_bwd_prep(Kzzbar, Kzz, r2, None)                       # Kzzbar <- Kzzbar * Kzz ; row sums
+  Gz2 = new(H, C, P, D)
+  ops.gemm(Kzzbar, zs, Gz2)
+  Gz1 = Gx = None
+  if have_data:
+    ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                      # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
+    Gz1 = new(H, C, P, D)
+    ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1)
+    if need_x_grad:
+      Gx = new(H, C, B, D)
+      ops.gemm(Kxbar.transpose(-1, -2), zs, Gx)
+  Z_bar = new(C, P, D)
+  ops.rbf_bwd_finish(zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar)
+  x_bar = None
+  if have_data:
+    x_bar = new(B, D) if need_x_grad else None
+    ops.rbf_bwd_xside(xs, csum, Gx, theta, theta_bar, x_bar)
+  return theta_bar, Z_bar, x_bar, m_bar, Lu_bar
