@@ -1,0 +1,148 @@
+/*
+ * libvargp_sm100.so -- C ABI of the B200-native VAR-GP ELBO hot path.
+ *
+ * The reference (uber-research/vargp) has no FFI: its hot path is ATen calls issued from
+ * var_gp/{kernels,gp_utils,likelihoods,vargp}.py.  Each entry point below replaces a group of those call
+ * sites (cited as file:line relative to the reference root); INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to call it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated otherwise; sizes and strides are int64, in
+ *     ELEMENTS; `stream` is a cudaStream_t passed as void*.
+ *   - the library never allocates, frees or retains memory; all work is asynchronous on `stream`.
+ *   - return value: 0 ok, <0 invalid argument (see vargp_strerror), >0 a cudaError_t.
+ *   - H = hyper samples, C = classes (output GPs), P = inducing points per class over all tasks,
+ *     M = inducing points per task, S = P / M tasks, B = minibatch, D = input dims, F = likelihood samples.
+ *   - theta is (H, D+1): log lengthscales then log scale factor, exactly `kern_samples` of
+ *     var_gp/kernels.py:24.
+ */
+#ifndef VARGP_SM100_H_
+#define VARGP_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VARGP_TRI_NONE 0
+#define VARGP_TRI_LOWER 1
+#define VARGP_TRI_UPPER 2
+
+#define VARGP_EPI_NONE 0
+#define VARGP_EPI_RBF 1      /* C = gamma2 * exp(acc - row[m]/2 - col[n]/2)                  */
+#define VARGP_EPI_RBF_SYM 2  /* same, and C[m][m] = gamma2 exactly (var_gp/kernels.py:47-48,54) */
+
+/* Batched strided GEMM  C = alpha * tri_a(A) * tri_b(B) [restricted to tri_c] + beta * C.
+ * A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs], C(m,n) = C[m*c_rs + n*c_cs].
+ * Up to three batch dimensions (nb[0] slowest); a stride of 0 broadcasts an operand.
+ * tri_a / tri_b declare structural zeros (the kernel never reads the other triangle);
+ * tri_c writes only that triangle (the other is zero-filled when beta == 0, left untouched otherwise).
+ * Replaces the einsum / bmm / triangular_solve call sites of var_gp/gp_utils.py:89-96,124-136,175-184
+ * (every TRSM there becomes a GEMM with the explicit inverse factor W = chol(K)^-1). */
+typedef struct {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t M, N, K;
+  int64_t a_rs, a_cs, b_rs, b_cs, c_rs, c_cs;
+  int64_t nb[3];
+  int64_t a_bs[3], b_bs[3], c_bs[3];
+  float alpha, beta;
+  int32_t tri_a, tri_b, tri_c;
+  /* optional fused epilogue (VARGP_EPI_*): row/col vectors are indexed like C's rows/cols */
+  int32_t epi;
+  const float* e_row;   /* (.., M) */
+  const float* e_col;   /* (.., N) */
+  int64_t e_row_bs[3], e_col_bs[3];
+  const float* e_theta; /* gamma2 = exp(2 * e_theta[batch offset via e_theta_bs + e_D]) */
+  int64_t e_theta_bs[3], e_D;
+} vargp_gemm_t;
+
+int vargp_init(int device);
+const char* vargp_version(void);
+const char* vargp_strerror(int code);
+/* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
+int64_t vargp_launch_count(void);
+
+int vargp_gemm(const vargp_gemm_t* g, void* stream);
+
+/* tcgen05 / TMA path (3xTF32): same contract as vargp_gemm restricted to K-contiguous operands
+ * (a_cs == 1, b_rs == 1), 16-byte aligned rows; returns -2 if the problem does not qualify. */
+int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
+
+/* dst[h][r][:] = src[r][:] * exp(-theta[h][:D]);  norms[h][r] = |dst[h][r]|^2.
+ * Replaces the `x / sigma` broadcasts and the Gram diagonals of var_gp/kernels.py:41-44,50-51,54. */
+int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t src_rs,
+                     const float* theta, int64_t H, int64_t theta_rs,
+                     float* dst, float* norms, void* stream);
+
+/* L = chol(A + jitter*I) (lower; strict upper zeroed), batched; info[b] = 0 or 1 + index of the first
+ * non-positive pivot.  A and L are (batch, n, n) with leading dimension ld and batch stride bs; may alias.
+ * Replaces var_gp/gp_utils.py:5-11. */
+int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+               int64_t n, int64_t batch, float jitter, int32_t* info, void* stream);
+
+/* W = L^-1 (lower; strict upper zeroed), batched.  Stands in for every torch.triangular_solve of
+ * var_gp/gp_utils.py (89,92,124,125,129,134,175,176,182). */
+int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_ld, int64_t w_bs,
+                int64_t n, int64_t batch, void* stream);
+
+/* packed row-major lower triangle -> (C, M, M) with softplus on the diagonal, and its adjoint.
+ * Replaces var_gp/gp_utils.py:22-49. */
+int vargp_tril_unpack(const float* vec, int64_t C, int64_t M, float* out, void* stream);
+int vargp_tril_unpack_bwd(const float* Lbar, const float* vec, int64_t C, int64_t M, float* vec_bar, void* stream);
+
+/* kl += (1/H) sum_hc [ -sum_{i in last block} log W_ii - sum_i log Lu_ii + (|T_last|_F^2 + |nu_last|^2 - M)/2 ]
+ * W (H,C,P,P), T (H,C,S,M,M), nu (H,C,P), Lu (C,M,M).  Replaces var_gp/vargp.py:182-190. */
+int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu,
+                 int64_t H, int64_t C, int64_t P, int64_t M, float* kl, void* stream);
+int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g_kl,
+                 int64_t H, int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream);
+int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar, void* stream);
+
+/* f_mean[g][b] = sum_p nu[g][p] V[g][p][b];
+ * f_var[g][b] = gamma2 - sum V^2 + sum TV^2 + jitter * sum A^2.   (var_gp/gp_utils.py:178-186) */
+int vargp_marginal_reduce(const float* V, const float* TV, const float* A, const float* nu,
+                          const float* theta, int64_t theta_rs, int64_t D,
+                          int64_t H, int64_t C, int64_t P, int64_t B, float jitter,
+                          float* f_mean, float* f_var, void* stream);
+/* Vbar = nu gm^T - 2 V gv;  A *= 2 jitter gv;  TV *= 2 gv;  theta_bar[h][D] += 2 gamma2 sum_cb gv */
+int vargp_marginal_bwd_prep(const float* V, float* TV, float* A, const float* nu,
+                            const float* g_mean, const float* g_var,
+                            const float* theta, int64_t theta_rs, int64_t D,
+                            int64_t H, int64_t C, int64_t P, int64_t B, float jitter,
+                            float* Vbar, float* theta_bar, void* stream);
+
+/* X <- (Phi(X) + Phi(X)^T)/2 in place, batch of n x n (only the lower triangle of X is read) */
+int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream);
+
+/* Kbar *= K (elementwise, in place); rsum[g][i] = row sums; csum[h][j] += sum over (c,i) (optional).
+ * Kbar, K are (H, C, Pa, Pb). */
+int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_t C, int64_t Pa, int64_t Pb,
+                       float* rsum, float* csum, void* stream);
+/* zs_bar = -(r1 + 2 r2) zs + Gz1 + 2 Gz2;  Zbar[c][i][d] = sum_h zs_bar * exp(-theta[h][d]);
+ * theta_bar[h][d] += sum_ci (-zs zs_bar - zs Gz1);  theta_bar[h][D] += 2 sum_ci (r1 + r2).  (Gz1, r1) and (Gz2, r2) may each be NULL pairs. */
+int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const float* Gz2, const float* r1, const float* r2,
+                         const float* theta, int64_t theta_rs, int64_t H, int64_t C, int64_t P, int64_t D,
+                         float* Zbar, float* theta_bar, void* stream);
+/* theta_bar[h][d] += sum_j csum[h][j] xs[h][j][d]^2;  optionally
+ * xbar[j][d] = sum_h (-csum xs + sum_c Gx[h][c][j][d]) exp(-theta[h][d])   (Gx, xbar may be NULL) */
+int vargp_rbf_bwd_xside(const float* xs, const float* csum, const float* Gx,
+                        const float* theta, int64_t theta_rs, int64_t H, int64_t C, int64_t B, int64_t D,
+                        float* theta_bar, float* xbar, void* stream);
+
+/* Monte-Carlo softmax likelihood (var_gp/likelihoods.py:13-47), forward and adjoint in one pass:
+ * nll += -(1/HF) sum_hfb log softmax_C(f_mean + sqrt(f_var) eps)[y_b];  g_mean, g_var = d nll / d(f_mean, f_var).
+ * eps (H,F,C,B); y int64 (B). */
+int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps, const int64_t* y,
+                      int64_t H, int64_t F, int64_t C, int64_t B,
+                      float* nll, float* g_mean, float* g_var, void* stream);
+/* probs[b][c] = (1/HF) sum_hf softmax_C(f)[c]   (var_gp/likelihoods.py:49-63) */
+int vargp_softmax_predict(const float* f_mean, const float* f_var, const float* eps,
+                          int64_t H, int64_t F, int64_t C, int64_t B, float* probs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VARGP_SM100_H_ */

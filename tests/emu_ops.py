@@ -96,14 +96,14 @@ class EmuOps:
 
   def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar):
     D = zs.shape[-1]
-    r = (r1 + 2. * r2).unsqueeze(-1)
-    zsb = -r * zs + 2. * Gz2
-    acc = -zs * zsb
-    if Gz1 is not None:
-      zsb = zsb + Gz1
-      acc = -zs * zsb - zs * Gz1
+    z0 = torch.zeros_like(zs)
+    r1 = torch.zeros_like(zs[..., 0]) if Gz1 is None else r1
+    r2 = torch.zeros_like(zs[..., 0]) if Gz2 is None else r2
+    g1 = z0 if Gz1 is None else Gz1
+    g2 = z0 if Gz2 is None else Gz2
+    zsb = -(r1 + 2. * r2).unsqueeze(-1) * zs + g1 + 2. * g2
     Z_bar.copy_((zsb * torch.exp(-theta[:, :D]).view(-1, 1, 1, D)).sum(0))
-    theta_bar[:, :D] += acc.sum((1, 2))
+    theta_bar[:, :D] += (-zs * zsb - zs * g1).sum((1, 2))
     theta_bar[:, D] += 2. * (r1 + r2).sum((1, 2))
 
   def rbf_bwd_xside(self, xs, csum, Gx, theta, theta_bar, x_bar):

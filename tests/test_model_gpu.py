@@ -1,0 +1,142 @@
+"""GPU parity of the product model (vargp_b200.VARGP on libvargp_sm100.so) against the reference fixtures.
+
+Tolerances are the north star's: ELBO terms and gradients rtol 1e-4 in fp32 (norm-relative), predictive
+probabilities 1e-5 absolute.  On the ill-conditioned toy cases the reference's own fp32 run is farther than
+that from its fp64 run, so there the bound is max(1e-4, 3 x the reference's fp32 error).
+"""
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _bound(ref32, ref64, key=None, base=1e-4):
+  a = ref32[key] if key else ref32
+  b = ref64[key] if key else ref64
+  return max(base, 3.0 * util.relerr(a, b))
+
+
+@pytest.mark.parametrize('name', util.golden_names())
+def test_loss_and_grads_match_reference(name, cuda_ops):
+  rec = util.load_golden(name)
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  r32, r64 = rec['f32'], rec['f64']
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  terms, grads = util.run_model(gp, x, y, noise, r64['beta'], r64['Ntot'])
+  for k in ('kl_hypers', 'kl_u', 'nll', 'total'):
+    if r64[k].abs() > 0:
+      err = util.relerr(terms[k], r64[k])
+      assert err < _bound(r32, r64, k), f'{name} {k}: {err:.3e}'
+  for k in util.GRAD_KEYS:
+    if r64['grads'][k].abs().max() > 0:
+      err = util.relerr(grads[k], r64['grads'][k])
+      assert err < _bound(r32['grads'], r64['grads'], k), f'{name} grad {k}: {err:.3e}'
+
+
+@pytest.mark.parametrize('name', util.golden_names())
+def test_predict_matches_reference(name, cuda_ops):
+  rec = util.load_golden(name)
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  with torch.no_grad():
+    probs = gp.predict(x.cuda(), noise={k: v.cuda() for k, v in noise.items()})
+    mu, var = gp(x.cuda(), noise={k: v.cuda() for k, v in noise.items()})
+  ref32, ref64 = rec['f32'], rec['f64']
+  tol = max(1e-5, 3.0 * (ref32['probs'].double() - ref64['probs']).abs().max().item())
+  err = (probs.double().cpu() - ref64['probs']).abs().max().item()
+  assert err < tol, f'{name} probs: {err:.3e} (tol {tol:.1e})'
+  assert util.relerr(mu, ref64['f_mean']) < _bound(ref32, ref64, 'f_mean')
+  assert util.relerr(var, ref64['f_var']) < _bound(ref32, ref64, 'f_var')
+  assert abs(float(probs.sum(-1).mean()) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize('name', ['mnist_t1', 'odd_t2'])
+def test_composed_path_agrees_with_fused(name, cuda_ops):
+  """forward(x, loss_cache=dict) (reference op order on the library) vs the fused whitened schedule."""
+  rec = util.load_golden(name)
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  nz = {k: v.cuda() for k, v in noise.items()}
+  from vargp_b200.composed import loss_composed
+  kl_h, kl_u, nll = loss_composed(gp, x.cuda(), y.cuda(), nz)
+  total = kl_u + 10. * nll
+  gp.zero_grad(); total.backward()
+  g_c = util.model_grads(gp)
+  g_c = {k: v.clone() for k, v in g_c.items()}
+  kl_h2, kl_u2, nll2 = gp.loss(x.cuda(), y.cuda(), noise=nz)
+  total2 = kl_u2 + 10. * nll2
+  gp.zero_grad(); total2.backward()
+  g_f = util.model_grads(gp)
+  assert util.relerr(kl_u2, kl_u) < 1e-4 and util.relerr(nll2, nll) < 1e-4
+  for k in util.GRAD_KEYS:
+    assert util.relerr(g_f[k], g_c[k]) < 2e-4, k
+
+
+def test_split_mnist_shape_against_oracle(cuda_ops):
+  """BASELINE configs[1] at full size (C=10, D=784, M=60, B=512, task 2): CUDA path vs the fp64 oracle."""
+  from oracle import vargp_oracle as orc
+  kw = dict(C=10, D=784, M=60, t=2, B=512, sigma=10., seed=77)
+  p64, prev64, x64, y, n64 = orc.make_case(dtype=torch.float64, **kw)
+  leaf = {k: (v.clone().requires_grad_(True) if k in util.GRAD_KEYS else v) for k, v in p64.items()}
+  kl_h, kl_u, nll = orc.elbo_terms(leaf, prev64, x64, y, n64, n_v=3)
+  (10. * kl_h + kl_u + 20. * nll).backward()
+  params, prev, x, y, noise = orc.make_case(dtype=torch.float32, **kw)
+  gp = util.build_model(params, prev, 3, 10, {}, 'cuda', torch.float32)
+  terms, grads = util.run_model(gp, x, y, noise, 10., 20. * 512)
+  assert util.relerr(terms['kl_u'], kl_u) < 1e-4
+  assert util.relerr(terms['nll'], nll) < 1e-4
+  for k in util.GRAD_KEYS:
+    assert util.relerr(grads[k], leaf[k].grad) < 1e-4, k
+  probs = gp.predict(x.cuda(), noise={k: v.cuda() for k, v in noise.items()})
+  pref = orc.predict(p64, prev64, x64, n64, n_v=3)
+  assert (probs.double().cpu() - pref).abs().max().item() < 1e-5
+
+
+def test_non_pd_raises_linalg_error(cuda_ops):
+  rec = util.load_golden('odd_t2')
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  params['z'][:] = float('nan')
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  with pytest.raises(torch.linalg.LinAlgError):
+    gp.loss(x.cuda(), y.cuda(), noise={k: v.cuda() for k, v in noise.items()})
+
+
+def test_rng_draw_order_matches_reference(cuda_ops):
+  """With no pinned noise the model must consume the global CUDA generator exactly like the reference:
+  (H, D+1) normal_ -> (n_v, H, C, Q) normal_ -> randn (H, F, C, B)   (SURVEY.md section 8c)."""
+  rec = util.load_golden('odd_t2')
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  H, C, M, t, B, D = 2, 3, 7, 2, 33, 37
+  torch.manual_seed(123)
+  e1 = torch.empty(H, D + 1, device='cuda').normal_()
+  e2 = torch.empty(n_v, H, C, t * M, device='cuda').normal_()
+  e3 = torch.randn(H, F, C, B, device='cuda')
+  a = gp.loss(x.cuda(), y.cuda(), noise=dict(eps_theta=e1, eps_u=e2, eps_f=e3))
+  torch.manual_seed(123)
+  b = gp.loss(x.cuda(), y.cuda())
+  for u, v in zip(a, b):
+    assert torch.equal(u, v)
+
+
+def test_linearity_and_idempotence_at_scale(cuda_ops):
+  """Size-independent properties at a larger shape than the oracle checks (P=500, B=2048):
+  the same inputs give bit-identical outputs twice, and the NLL is additive over minibatch halves."""
+  from oracle import vargp_oracle as orc
+  params, prev, x, y, noise = orc.make_case(C=10, D=784, M=100, t=4, B=2048, sigma=10., seed=5)
+  gp = util.build_model(params, prev, 3, 10, {}, 'cuda', torch.float32)
+  nz = {k: v.cuda() for k, v in noise.items()}
+  xc, yc = x.cuda(), y.cuda()
+  a = gp.loss(xc, yc, noise=nz)
+  b = gp.loss(xc, yc, noise=nz)
+  assert torch.equal(a[1], b[1])
+  assert abs(float(a[2] - b[2])) <= 1e-6 * abs(float(a[2]))     # nll sums with atomics
+  h = 1024
+  n1 = dict(nz, eps_f=nz['eps_f'][..., :h].contiguous())
+  n2 = dict(nz, eps_f=nz['eps_f'][..., h:].contiguous())
+  l1 = gp.loss(xc[:h], yc[:h], noise=n1)
+  l2 = gp.loss(xc[h:], yc[h:], noise=n2)
+  assert util.relerr(l1[2] + l2[2], a[2]) < 1e-5
+  assert util.relerr(l1[1], a[1]) < 1e-6

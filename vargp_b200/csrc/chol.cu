@@ -1,0 +1,255 @@
+// Batched Cholesky L = chol(A + jitter I) and triangular inverse W = L^-1, one CTA per matrix.
+//
+// Left-looking over 32-wide block columns.  Thread r owns row r of the current panel: its 32 panel
+// entries live in registers, the 32x32 block shared by all rows is staged in shared memory and read as
+// warp-broadcast float4 (one wavefront per 4 FMAs x 32 lanes), the diagonal block is factored by one
+// warp with register shuffles.  The matrices of the Split/Permuted-MNIST shapes (P <= 1000, 30 of them)
+// stay L2-resident; the bound is FMA issue + latency, not HBM (AI = P/24 flop/B).
+// Larger P is driven block-wise from the host schedule (GEMM-based trailing updates), which calls these
+// kernels on the diagonal blocks only.
+#include "common.cuh"
+
+namespace vargp {
+
+constexpr int NB = 32;
+constexpr int kCholThreads = 512;
+
+__device__ __forceinline__ void load_row32(const float* p, float (&a)[NB], int valid) {
+  // p points at 32 consecutive floats of one row (not necessarily 16-byte aligned)
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = (c < valid) ? p[c] : 0.f;
+}
+
+__global__ void __launch_bounds__(kCholThreads)
+chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l_ld,
+            int64_t l_bs, int n, float jitter, int32_t* __restrict__ info) {
+  __shared__ __align__(16) float Bs[NB][NB + 4];   // Bs[kk][c] = L[k0 + c][kc + kk]   (transposed block)
+  __shared__ __align__(16) float Ds[NB][NB + 4];   // factored diagonal block, Ds[j][l] = Lkk[j][l]
+  __shared__ float Dinv[NB];
+  __shared__ int s_info;
+
+  const float* A = Ain + (int64_t)blockIdx.x * a_bs;
+  float* L = Lout + (int64_t)blockIdx.x * l_bs;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_info = 0;
+
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nbk = min(NB, n - k0);     // live columns of this block column
+    const int R = n - k0;                // live rows (diag block first)
+    for (int r0 = 0; r0 < R; r0 += kCholThreads) {
+      const int r = r0 + tid;
+      const bool live = r < R;
+      float acc[NB];
+      if (live) {
+        load_row32(A + (int64_t)(k0 + r) * a_ld + k0, acc, nbk);
+        if (r < NB) acc[r] += jitter;                       // r < nbk here because r < R
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] = 0.f;
+      }
+      // ---- left-looking update: acc[c] -= sum_{k<k0} L[k0+r][k] * L[k0+c][k] ----
+      for (int kc = 0; kc < k0; kc += NB) {
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += kCholThreads) {
+          const int c = e / NB, kk = e % NB;
+          Bs[kk][c] = (c < nbk) ? L[(int64_t)(k0 + c) * l_ld + kc + kk] : 0.f;
+        }
+        __syncthreads();
+        if (live) {
+          float a[NB];
+          load_row32(L + (int64_t)(k0 + r) * l_ld + kc, a, NB);
+#pragma unroll
+          for (int kk = 0; kk < NB; ++kk) {
+#pragma unroll
+            for (int c4 = 0; c4 < NB; c4 += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][c4]);
+              acc[c4 + 0] = fmaf(-a[kk], b.x, acc[c4 + 0]);
+              acc[c4 + 1] = fmaf(-a[kk], b.y, acc[c4 + 1]);
+              acc[c4 + 2] = fmaf(-a[kk], b.z, acc[c4 + 2]);
+              acc[c4 + 3] = fmaf(-a[kk], b.w, acc[c4 + 3]);
+            }
+          }
+        }
+      }
+      if (r0 == 0) {
+        // ---- factor the 32x32 diagonal block in warp 0 (lane i = row i) ----
+        if (tid < NB) {
+          const int lane = tid;
+          if (lane >= nbk) {                                   // virtual identity rows past the edge
+#pragma unroll
+            for (int c = 0; c < NB; ++c) acc[c] = (c == lane) ? 1.f : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float d = __shfl_sync(0xffffffffu, acc[j], j);
+            if (!(d > 0.f) && lane == 0 && j < nbk && s_info == 0) s_info = k0 + j + 1;
+            const float dj = sqrtf(d);
+            const float inv = 1.f / dj;
+            if (lane == j) acc[j] = dj;
+            if (lane > j) acc[j] *= inv;
+            const float lij = acc[j];
+#pragma unroll
+            for (int c = j + 1; c < NB; ++c) {
+              const float lcj = __shfl_sync(0xffffffffu, lij, c);
+              if (lane >= c) acc[c] = fmaf(-lij, lcj, acc[c]);
+            }
+            if (lane == j) Dinv[j] = inv;
+          }
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            if (c > lane) acc[c] = 0.f;
+            Ds[lane][c] = acc[c];
+          }
+        }
+        __syncthreads();
+      }
+      // ---- panel solve for rows below the diagonal block: x Lkk^T = a ----
+      if (live && r >= NB) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          float s = acc[j];
+#pragma unroll
+          for (int l4 = 0; l4 < j; l4 += 4) {
+            const float4 dd = *reinterpret_cast<const float4*>(&Ds[j][l4]);
+            s = fmaf(-acc[l4 + 0], dd.x, s);
+            if (l4 + 1 < j) s = fmaf(-acc[l4 + 1], dd.y, s);
+            if (l4 + 2 < j) s = fmaf(-acc[l4 + 2], dd.z, s);
+            if (l4 + 3 < j) s = fmaf(-acc[l4 + 3], dd.w, s);
+          }
+          acc[j] = s * Dinv[j];
+        }
+      }
+      if (live) {
+        float* lp = L + (int64_t)(k0 + r) * l_ld + k0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          if (c < nbk) lp[c] = acc[c];
+      }
+    }
+    // zero the strict upper part to the right of the diagonal block
+    const int ncols = n - (k0 + NB);
+    if (ncols > 0) {
+      for (int e = tid; e < nbk * ncols; e += kCholThreads) {
+        const int rr = e / ncols, cc = e % ncols;
+        L[(int64_t)(k0 + rr) * l_ld + k0 + NB + cc] = 0.f;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && info) info[blockIdx.x] = s_info;
+}
+
+// W = L^-1.  Top-down over 32-row blocks; thread j owns column j of the block row being produced:
+// W[k][j] = -Wkk * sum_{l<k} L[k][l] W[l][j], with W[l][j] read coalesced across threads.
+__global__ void __launch_bounds__(kCholThreads)
+trtri_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld,
+             int64_t w_bs, int n) {
+  __shared__ __align__(16) float Lb[NB][NB + 4];   // Lb[kk][c] = L[k0 + c][lc + kk]
+  __shared__ __align__(16) float Ls[NB][NB + 4];   // diagonal block of L
+  __shared__ __align__(16) float Ws[NB][NB + 4];   // its inverse, Ws[c][c'] = Wkk[c][c']
+
+  const float* L = Lin + (int64_t)blockIdx.x * l_bs;
+  float* W = Wout + (int64_t)blockIdx.x * w_bs;
+  const int tid = threadIdx.x;
+
+  // zero-fill the strict upper triangle (the block rows below only write j <= row)
+  for (int64_t e = tid; e < (int64_t)n * n; e += kCholThreads) {
+    const int i = (int)(e / n), j = (int)(e % n);
+    if (j > i) W[(int64_t)i * w_ld + j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nbk = min(NB, n - k0);
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += kCholThreads) {
+      const int i = e / NB, j = e % NB;
+      float v = (i == j) ? 1.f : 0.f;
+      if (i < nbk && j < nbk && j <= i) v = L[(int64_t)(k0 + i) * l_ld + k0 + j];
+      Ls[i][j] = v;
+    }
+    __syncthreads();
+    if (tid < NB) {
+      // lane j solves Lkk x = e_j
+      const int j = tid;
+      float x[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        float s = (i == j) ? 1.f : 0.f;
+#pragma unroll
+        for (int l = 0; l < i; ++l) s = fmaf(-Ls[i][l], x[l], s);
+        x[i] = (i >= j) ? s / Ls[i][i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) Ws[i][j] = x[i];
+    }
+    __syncthreads();
+    // diagonal block of W
+    for (int e = tid; e < nbk * nbk; e += kCholThreads) {
+      const int i = e / nbk, j = e % nbk;
+      if (j <= i) W[(int64_t)(k0 + i) * w_ld + k0 + j] = Ws[i][j];
+    }
+    // off-diagonal part of block row k: columns j < k0
+    for (int j0 = 0; j0 < k0; j0 += kCholThreads) {
+      const int j = j0 + tid;
+      const bool live = j < k0;
+      float acc[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = 0.f;
+      const int lc_begin = (j0 / NB) * NB;          // first chunk any thread of this pass can need
+      for (int lc = lc_begin; lc < k0; lc += NB) {
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += kCholThreads) {
+          const int c = e / NB, kk = e % NB;
+          Lb[kk][c] = (c < nbk) ? L[(int64_t)(k0 + c) * l_ld + lc + kk] : 0.f;
+        }
+        __syncthreads();
+        if (live && lc + NB > j) {
+#pragma unroll
+          for (int kk = 0; kk < NB; ++kk) {
+            const float w = W[(int64_t)(lc + kk) * w_ld + j];   // zero above the diagonal
+#pragma unroll
+            for (int c4 = 0; c4 < NB; c4 += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(&Lb[kk][c4]);
+              acc[c4 + 0] = fmaf(w, b.x, acc[c4 + 0]);
+              acc[c4 + 1] = fmaf(w, b.y, acc[c4 + 1]);
+              acc[c4 + 2] = fmaf(w, b.z, acc[c4 + 2]);
+              acc[c4 + 3] = fmaf(w, b.w, acc[c4 + 3]);
+            }
+          }
+        }
+      }
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          if (c < nbk) {
+            float s = 0.f;
+#pragma unroll
+            for (int cp = 0; cp <= c; ++cp) s = fmaf(Ws[c][cp], acc[cp], s);
+            W[(int64_t)(k0 + c) * w_ld + j] = -s;
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace vargp
+
+using namespace vargp;
+
+extern "C" int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                          int64_t n, int64_t batch, float jitter, int32_t* info, void* stream) {
+  if (!A || !L || n < 1 || batch < 1 || a_ld < n || l_ld < n) return VARGP_ERR_ARG;
+  if (n > (1 << 20)) return VARGP_ERR_UNSUPPORTED;
+  chol_kernel<<<(unsigned)batch, kCholThreads, 0, (cudaStream_t)stream>>>(A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
+                                                                          jitter, info);
+  return launch_status();
+}
+
+extern "C" int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_ld, int64_t w_bs,
+                           int64_t n, int64_t batch, void* stream) {
+  if (!L || !W || n < 1 || batch < 1 || l_ld < n || w_ld < n) return VARGP_ERR_ARG;
+  if (L == W) return VARGP_ERR_ARG;
+  trtri_kernel<<<(unsigned)batch, kCholThreads, 0, (cudaStream_t)stream>>>(L, l_ld, l_bs, W, w_ld, w_bs, (int)n);
+  return launch_status();
+}

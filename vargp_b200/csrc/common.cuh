@@ -1,0 +1,43 @@
+// Shared helpers for libvargp_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vargp_sm100.h"
+
+namespace vargp {
+
+extern int64_t g_launches;   // counted on the host at every kernel launch (bench.py: gpu_launches)
+
+#define VARGP_ERR_ARG (-1)
+#define VARGP_ERR_UNSUPPORTED (-2)
+#define VARGP_ERR_NOT_INIT (-3)
+
+inline int launch_status() {
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? 0 : (int)cudaGetLastError();
+}
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0 (and broadcast to all when `all` is set). scratch: >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.f;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+}  // namespace vargp

@@ -1,0 +1,241 @@
+// ARD-RBF kernel: operand scaling / norms (forward) and the adjoint passes that turn Kbar into
+// gradients for z, x and theta.  All of these are streaming (HBM / L2 bound) SIMT kernels; the only
+// dense contractions of the RBF path (x.z^T forward, W.X backward) are GEMMs (gemm_simt.cu / gemm_tc.cu).
+#include "common.cuh"
+
+namespace vargp {
+
+// ---------------------------------------------------------------------------------------------
+// dst[h][r][d] = src[r][d] * exp(-theta[h][d]); norms[h][r] = sum_d dst^2     (kernels.py:41-44,50,54)
+// grid (row blocks, H); one warp per row, lanes stride over d (coalesced 128 B per request).
+// Algorithmic bytes: 4*(R*D read + H*R*D written + H*R).
+// ---------------------------------------------------------------------------------------------
+constexpr int kScaleWarps = 8;
+constexpr int kScaleRowsPerWarp = 4;
+
+__global__ void __launch_bounds__(kScaleWarps * 32)
+scale_rows_kernel(const float* __restrict__ src, int64_t R, int64_t D, int64_t src_rs,
+                  const float* __restrict__ theta, int64_t theta_rs,
+                  float* __restrict__ dst, float* __restrict__ norms) {
+  extern __shared__ __align__(16) float s_isig[];
+  const int h = blockIdx.y;
+  for (int64_t d = threadIdx.x; d < D; d += blockDim.x) s_isig[d] = expf(-theta[h * theta_rs + d]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t row0 = ((int64_t)blockIdx.x * kScaleWarps + wid) * kScaleRowsPerWarp;
+  const bool vec4 = (D % 4 == 0) && (src_rs % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0);
+#pragma unroll
+  for (int rr = 0; rr < kScaleRowsPerWarp; ++rr) {
+    const int64_t r = row0 + rr;
+    if (r >= R) break;
+    const float* sp = src + r * src_rs;
+    float* dp = dst + ((int64_t)h * R + r) * D;
+    float acc = 0.f;
+    if (vec4) {
+      for (int64_t d = lane * 4; d < D; d += 128) {
+        float4 v = *reinterpret_cast<const float4*>(sp + d);
+        const float4 s = *reinterpret_cast<const float4*>(s_isig + d);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+        *reinterpret_cast<float4*>(dp + d) = v;
+      }
+    } else {
+      for (int64_t d = lane; d < D; d += 32) {
+        const float v = sp[d] * s_isig[d];
+        acc = fmaf(v, v, acc);
+        dp[d] = v;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) norms[(int64_t)h * R + r] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kbar <- Kbar * K; rsum[g][i] = sum_j; csum[h][j] += sum_{c,i}            (W = Kbar (.) K)
+// grid (row tiles, G); a block owns RT rows x all columns, threads stride over columns.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepRT = 16;
+constexpr int kPrepThreads = 256;
+
+__global__ void __launch_bounds__(kPrepThreads)
+rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64_t C, int64_t Pa, int64_t Pb,
+                    float* __restrict__ rsum, float* __restrict__ csum) {
+  __shared__ float s_red[kPrepRT][kPrepThreads / 32];
+  const int64_t g = blockIdx.y;
+  const int64_t h = g / C;
+  const int64_t i0 = (int64_t)blockIdx.x * kPrepRT;
+  const int rows = (int)min((int64_t)kPrepRT, Pa - i0);
+  float* kb = Kbar + (g * Pa + i0) * Pb;
+  const float* kk = K + (g * Pa + i0) * Pb;
+  float racc[kPrepRT];
+#pragma unroll
+  for (int r = 0; r < kPrepRT; ++r) racc[r] = 0.f;
+  for (int64_t j = threadIdx.x; j < Pb; j += kPrepThreads) {
+    float cacc = 0.f;
+#pragma unroll
+    for (int r = 0; r < kPrepRT; ++r) {
+      if (r < rows) {
+        const float w = kb[(int64_t)r * Pb + j] * kk[(int64_t)r * Pb + j];
+        kb[(int64_t)r * Pb + j] = w;
+        racc[r] += w;
+        cacc += w;
+      }
+    }
+    if (csum) atomicAdd(csum + h * Pb + j, cacc);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < kPrepRT; ++r) {
+    const float v = warp_sum(racc[r]);
+    if (lane == 0) s_red[r][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < rows) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPrepThreads / 32; ++w) v += s_red[threadIdx.x][w];
+    rsum[g * Pa + i0 + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// zs_bar = -(r1 + 2 r2) zs + Gz1 + 2 Gz2 ; Zbar[c][i][d] = sum_h zs_bar exp(-theta[h][d])
+// theta_bar[h][d] += sum_{c,i} (-zs zs_bar - zs Gz1) ; theta_bar[h][D] += 2 sum_{c,i} (r1 + r2)
+// grid (D tiles, row tiles over C*P); thread = one d, loops h (outer) and the block's rows (inner).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinRows = 8;
+constexpr int kFinThreads = 128;
+
+__global__ void __launch_bounds__(kFinThreads)
+rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz1, const float* __restrict__ Gz2,
+                      const float* __restrict__ r1, const float* __restrict__ r2,
+                      const float* __restrict__ theta, int64_t theta_rs, int64_t H, int64_t R, int64_t D,
+                      float* __restrict__ Zbar, float* __restrict__ theta_bar) {
+  const int64_t d = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.y * kFinRows;
+  const int rows = (int)min((int64_t)kFinRows, R - row0);
+  float zacc[kFinRows];
+#pragma unroll
+  for (int r = 0; r < kFinRows; ++r) zacc[r] = 0.f;
+  if (d < D) {
+    for (int64_t h = 0; h < H; ++h) {
+      const float isig = expf(-theta[h * theta_rs + d]);
+      float tacc = 0.f;
+#pragma unroll
+      for (int r = 0; r < kFinRows; ++r) {
+        if (r < rows) {
+          const int64_t row = h * R + row0 + r;
+          const float z = zs[row * D + d];
+          const float g1 = Gz1 ? Gz1[row * D + d] : 0.f;
+          const float g2 = Gz2 ? Gz2[row * D + d] : 0.f;
+          const float rr = (r1 ? r1[row] : 0.f) + 2.f * (r2 ? r2[row] : 0.f);
+          const float zb = fmaf(-rr, z, g1 + 2.f * g2);
+          zacc[r] = fmaf(zb, isig, zacc[r]);
+          tacc -= z * (zb + g1);
+        }
+      }
+      atomicAdd(theta_bar + h * (D + 1) + d, tacc);
+    }
+#pragma unroll
+    for (int r = 0; r < kFinRows; ++r)
+      if (r < rows) Zbar[(row0 + r) * D + d] = zacc[r];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < rows) {
+    for (int64_t h = 0; h < H; ++h) {
+      const int64_t row = h * R + row0 + threadIdx.x;
+      atomicAdd(theta_bar + h * (D + 1) + D, 2.f * ((r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f)));
+    }
+  }
+}
+
+// theta_bar[h][d] += sum_j csum[h][j] xs[h][j][d]^2     grid (D tiles, j tiles, H)
+constexpr int kXsRows = 64;
+__global__ void __launch_bounds__(128)
+rbf_bwd_xside_theta_kernel(const float* __restrict__ xs, const float* __restrict__ csum, int64_t B, int64_t D,
+                           float* __restrict__ theta_bar) {
+  const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t h = blockIdx.z;
+  const int64_t j0 = (int64_t)blockIdx.y * kXsRows;
+  const int64_t j1 = min(B, j0 + kXsRows);
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int64_t j = j0; j < j1; ++j) {
+    const float v = xs[(h * B + j) * D + d];
+    acc = fmaf(csum[h * B + j] * v, v, acc);
+  }
+  atomicAdd(theta_bar + h * (D + 1) + d, acc);
+}
+
+// xbar[j][d] = sum_h (-csum[h][j] xs[h][j][d] + sum_c Gx[h][c][j][d]) exp(-theta[h][d])
+__global__ void __launch_bounds__(128)
+rbf_bwd_xside_x_kernel(const float* __restrict__ xs, const float* __restrict__ csum, const float* __restrict__ Gx,
+                       const float* __restrict__ theta, int64_t theta_rs, int64_t H, int64_t C, int64_t B, int64_t D,
+                       float* __restrict__ xbar) {
+  const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int64_t h = 0; h < H; ++h) {
+    float v = -csum[h * B + j] * xs[(h * B + j) * D + d];
+    for (int64_t c = 0; c < C; ++c) v += Gx[(((h * C + c) * B) + j) * D + d];
+    acc = fmaf(v, expf(-theta[h * theta_rs + d]), acc);
+  }
+  xbar[j * D + d] = acc;
+}
+
+}  // namespace vargp
+
+using namespace vargp;
+
+extern "C" int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t src_rs,
+                                const float* theta, int64_t H, int64_t theta_rs,
+                                float* dst, float* norms, void* stream) {
+  if (!src || !theta || !dst || !norms || R < 0 || D < 1 || H < 1) return VARGP_ERR_ARG;
+  if (R == 0) return 0;
+  if (D * sizeof(float) > 48 * 1024) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(R, kScaleWarps * kScaleRowsPerWarp), (unsigned)H);
+  scale_rows_kernel<<<grid, kScaleWarps * 32, D * sizeof(float), (cudaStream_t)stream>>>(
+      src, R, D, src_rs, theta, theta_rs, dst, norms);
+  return launch_status();
+}
+
+extern "C" int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_t C, int64_t Pa, int64_t Pb,
+                                  float* rsum, float* csum, void* stream) {
+  if (!Kbar || !K || !rsum || H < 1 || C < 1 || Pa < 1 || Pb < 1) return VARGP_ERR_ARG;
+  if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(Pa, kPrepRT), (unsigned)(H * C));
+  rbf_bwd_prep_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(Kbar, K, C, Pa, Pb, rsum, csum);
+  return launch_status();
+}
+
+extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const float* Gz2, const float* r1,
+                                    const float* r2, const float* theta, int64_t theta_rs, int64_t H, int64_t C,
+                                    int64_t P, int64_t D, float* Zbar, float* theta_bar, void* stream) {
+  if (!zs || !theta || !Zbar || !theta_bar) return VARGP_ERR_ARG;
+  if ((Gz1 != nullptr) != (r1 != nullptr) || (Gz2 != nullptr) != (r2 != nullptr)) return VARGP_ERR_ARG;
+  const int64_t R = C * P;
+  if (ceil_div(R, kFinRows) > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows));
+  rbf_bwd_finish_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(zs, Gz1, Gz2, r1, r2, theta, theta_rs, H, R,
+                                                                         D, Zbar, theta_bar);
+  return launch_status();
+}
+
+extern "C" int vargp_rbf_bwd_xside(const float* xs, const float* csum, const float* Gx, const float* theta,
+                                   int64_t theta_rs, int64_t H, int64_t C, int64_t B, int64_t D,
+                                   float* theta_bar, float* xbar, void* stream) {
+  if (!xs || !csum || !theta || !theta_bar) return VARGP_ERR_ARG;
+  if ((xbar != nullptr) != (Gx != nullptr)) return VARGP_ERR_ARG;
+  if (ceil_div(B, kXsRows) > 65535 || H > 65535 || B > 65535 * 64) return VARGP_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(B, kXsRows), (unsigned)H);
+  rbf_bwd_xside_theta_kernel<<<grid, 128, 0, s>>>(xs, csum, B, D, theta_bar);
+  int rc = launch_status();
+  if (rc || !xbar) return rc;
+  if (B > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid2((unsigned)ceil_div(D, 128), (unsigned)B);
+  rbf_bwd_xside_x_kernel<<<grid2, 128, 0, s>>>(xs, csum, Gx, theta, theta_rs, H, C, B, D, xbar);
+  return launch_status();
+}

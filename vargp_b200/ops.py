@@ -1,13 +1,348 @@
-"""Kernel interface of the hot path (placeholder until the CUDA binding lands)."""
+"""ctypes binding of ``libvargp_sm100.so`` (include/vargp_sm100.h): the ONLY compute backend.
+
+``get_ops()`` returns the kernel interface used by the host schedule (``elbo.py``, ``gp_utils.py`` ...).
+Every method takes torch CUDA fp32 tensors (views allowed where the C entry point takes strides), checks
+them, and launches the kernel asynchronously on torch's current stream.  There is no CPU fallback: if the
+shared library is missing or the tensors are not on a B200, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libvargp_sm100.so')
+
+_TRI = {None: 0, 'lower': 1, 'upper': 2}
+EPI_NONE, EPI_RBF, EPI_RBF_SYM = 0, 1, 2
+
+i64 = ctypes.c_int64
+f32p = ctypes.c_void_p
+vp = ctypes.c_void_p
+
+
+class GemmDesc(ctypes.Structure):
+  """Mirror of vargp_gemm_t (include/vargp_sm100.h)."""
+  _fields_ = [
+    ('A', vp), ('B', vp), ('C', vp),
+    ('M', i64), ('N', i64), ('K', i64),
+    ('a_rs', i64), ('a_cs', i64), ('b_rs', i64), ('b_cs', i64), ('c_rs', i64), ('c_cs', i64),
+    ('nb', i64 * 3),
+    ('a_bs', i64 * 3), ('b_bs', i64 * 3), ('c_bs', i64 * 3),
+    ('alpha', ctypes.c_float), ('beta', ctypes.c_float),
+    ('tri_a', ctypes.c_int32), ('tri_b', ctypes.c_int32), ('tri_c', ctypes.c_int32),
+    ('epi', ctypes.c_int32),
+    ('e_row', vp), ('e_col', vp),
+    ('e_row_bs', i64 * 3), ('e_col_bs', i64 * 3),
+    ('e_theta', vp),
+    ('e_theta_bs', i64 * 3), ('e_D', i64),
+  ]
+
+
+class VargpError(RuntimeError):
+  pass
+
+
+def _load():
+  if not os.path.exists(_LIB_PATH):
+    raise VargpError(
+      f'{_LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+      f'(or vargp_b200/csrc/build.sh). vargp_b200 has no CPU / eager fallback.')
+  lib = ctypes.CDLL(_LIB_PATH)
+  lib.vargp_version.restype = ctypes.c_char_p
+  lib.vargp_strerror.restype = ctypes.c_char_p
+  lib.vargp_strerror.argtypes = [ctypes.c_int]
+  lib.vargp_launch_count.restype = i64
+  lib.vargp_init.argtypes = [ctypes.c_int]
+  lib.vargp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
+  lib.vargp_gemm_tc.argtypes = [ctypes.POINTER(GemmDesc), vp]
+  lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
+  lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
+  lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
+  lib.vargp_tril_unpack.argtypes = [vp, i64, i64, vp, vp]
+  lib.vargp_tril_unpack_bwd.argtypes = [vp, vp, i64, i64, vp, vp]
+  lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp]
+  lib.vargp_kl_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_kl_bwd_lu.argtypes = [vp, vp, i64, i64, vp, vp]
+  lib.vargp_marginal_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, ctypes.c_float, vp, vp, vp]
+  lib.vargp_marginal_bwd_prep.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64,
+                                          ctypes.c_float, vp, vp, vp]
+  lib.vargp_sym_phi.argtypes = [vp, i64, i64, vp]
+  lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp]
+  lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+  lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+  lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
+  return lib
+
+
+def _f32(t, name, contiguous=True):
+  if not isinstance(t, torch.Tensor) or t.dtype != torch.float32 or not t.is_cuda:
+    raise VargpError(f'{name}: expected a CUDA float32 tensor, got '
+                     f'{getattr(t, "dtype", type(t))} on {getattr(t, "device", "?")}')
+  if contiguous and not t.is_contiguous():
+    raise VargpError(f'{name}: expected a contiguous tensor, got strides {t.stride()} for shape {tuple(t.shape)}')
+  return t.data_ptr()
+
+
+def _bstrides(t, nbatch):
+  """Batch strides of `t` (last two dims are the matrix), left-padded to 3, 0 for broadcast dims."""
+  sizes, strides = list(t.shape[:-2]), list(t.stride()[:-2])
+  pad = 3 - len(sizes)
+  if pad < 0:
+    raise VargpError('at most 3 batch dimensions are supported')
+  sizes, strides = [1] * pad + sizes, [0] * pad + strides
+  out = []
+  for sz, st, nb in zip(sizes, strides, nbatch):
+    if sz == nb:
+      out.append(st if sz > 1 else 0)
+    elif sz == 1:
+      out.append(0)
+    else:
+      raise VargpError(f'batch dims {sizes} do not broadcast to {list(nbatch)}')
+  return out
+
+
+class CudaOps:
+  """Kernel interface backed by libvargp_sm100.so.  Contracts: see tests/emu_ops.py (same method names)
+  and include/vargp_sm100.h."""
+  name = 'sm100'
+
+  def __init__(self):
+    self.lib = _load()
+    if not torch.cuda.is_available():
+      raise VargpError('vargp_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+    self._inited = set()
+    self.use_tc = os.environ.get('VARGP_TC', '1') != '0'
+
+  # -- plumbing -------------------------------------------------------------------------------
+  def _stream(self, t):
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in self._inited:
+      self._check(self.lib.vargp_init(dev), 'vargp_init')
+      self._inited.add(dev)
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+  def _check(self, rc, what):
+    if rc != 0:
+      raise VargpError(f'{what} failed: {self.lib.vargp_strerror(rc).decode()} (code {rc})')
+
+  def launch_count(self):
+    return int(self.lib.vargp_launch_count())
+
+  # -- GEMM -----------------------------------------------------------------------------------
+  def _desc(self, A, B, C, alpha, beta, a_tri, b_tri, c_tri):
+    for t, nm in ((A, 'A'), (B, 'B'), (C, 'C')):
+      _f32(t, 'gemm ' + nm, contiguous=False)
+    M, K = A.shape[-2:]
+    K2, N = B.shape[-2:]
+    if K != K2 or tuple(C.shape[-2:]) != (M, N):
+      raise VargpError(f'gemm shape mismatch: A {tuple(A.shape)} B {tuple(B.shape)} C {tuple(C.shape)}')
+    cb = list(C.shape[:-2])
+    nb = [1] * (3 - len(cb)) + cb
+    d = GemmDesc()
+    d.A, d.B, d.C = A.data_ptr(), B.data_ptr(), C.data_ptr()
+    d.M, d.N, d.K = M, N, K
+    d.a_rs, d.a_cs = A.stride(-2), A.stride(-1)
+    d.b_rs, d.b_cs = B.stride(-2), B.stride(-1)
+    d.c_rs, d.c_cs = C.stride(-2), C.stride(-1)
+    d.nb = (i64 * 3)(*nb)
+    d.a_bs = (i64 * 3)(*_bstrides(A, nb))
+    d.b_bs = (i64 * 3)(*_bstrides(B, nb))
+    d.c_bs = (i64 * 3)(*_bstrides(C, nb))
+    d.alpha, d.beta = float(alpha), float(beta)
+    d.tri_a, d.tri_b, d.tri_c = _TRI[a_tri], _TRI[b_tri], _TRI[c_tri]
+    d.epi = EPI_NONE
+    return d, nb
+
+  def _run_gemm(self, d, ref):
+    s = self._stream(ref)
+    if self.use_tc:
+      rc = self.lib.vargp_gemm_tc(ctypes.byref(d), s)
+      if rc == 0:
+        return
+      if rc != -2:
+        self._check(rc, 'vargp_gemm_tc')
+    self._check(self.lib.vargp_gemm(ctypes.byref(d), s), 'vargp_gemm')
+
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None):
+    d, _ = self._desc(A, B, C, alpha, beta, a_tri, b_tri, c_tri)
+    self._run_gemm(d, C)
+
+  def rbf_gram(self, a, an, b, bn, theta, out, sym):
+    """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}."""
+    _f32(theta, 'theta', contiguous=False)
+    d, nb = self._desc(a, b.transpose(-1, -2), out, 1., 0., None, None, None)
+    _f32(an, 'an', contiguous=False)
+    _f32(bn, 'bn', contiguous=False)
+    if an.stride(-1) != 1 or bn.stride(-1) != 1 or theta.stride(-1) != 1:
+      raise VargpError('rbf_gram: norm vectors / theta must be contiguous in their last dim')
+    d.epi = EPI_RBF_SYM if sym else EPI_RBF
+    d.e_row, d.e_col = an.data_ptr(), bn.data_ptr()
+    d.e_row_bs = (i64 * 3)(*_bstrides(an.unsqueeze(-1), nb))
+    d.e_col_bs = (i64 * 3)(*_bstrides(bn.unsqueeze(-1), nb))
+    d.e_theta = theta.data_ptr()
+    H = theta.shape[0]
+    if out.dim() < 3 or out.shape[0] != H:
+      raise VargpError('rbf_gram: the leading batch dimension of `out` must be the hyper-sample index')
+    th = theta.as_strided((H,) + (1,) * (out.dim() - 3) + (1, 1), (theta.stride(0),) + (0,) * (out.dim() - 3) + (1, 1))
+    d.e_theta_bs = (i64 * 3)(*_bstrides(th, nb))
+    d.e_D = theta.shape[1] - 1
+    self._run_gemm(d, out)
+
+  # -- RBF operand prep / adjoint -------------------------------------------------------------
+  def scale_rows(self, src, theta, dst, norms):
+    _f32(src, 'src', contiguous=False)
+    if src.dim() != 2 or src.stride(1) != 1:
+      raise VargpError('scale_rows: src must be (R, D) with unit inner stride')
+    R, D = src.shape
+    H = theta.shape[0]
+    _f32(theta, 'theta', contiguous=False)
+    if theta.stride(1) != 1 or theta.shape[1] != D + 1:
+      raise VargpError('scale_rows: theta must be (H, D+1) with unit inner stride')
+    if tuple(dst.shape) != (H, R, D) or tuple(norms.shape) != (H, R):
+      raise VargpError('scale_rows: bad output shapes')
+    self._check(self.lib.vargp_scale_rows(src.data_ptr(), R, D, src.stride(0), theta.data_ptr(), H, theta.stride(0),
+                                          _f32(dst, 'dst'), _f32(norms, 'norms'), self._stream(dst)), 'scale_rows')
+
+  def rbf_bwd_prep(self, Kbar, K, rsum, csum):
+    H, C, Pa, Pb = K.shape
+    self._check(self.lib.vargp_rbf_bwd_prep(_f32(Kbar, 'Kbar'), _f32(K, 'K'), H, C, Pa, Pb, _f32(rsum, 'rsum'),
+                                            None if csum is None else _f32(csum, 'csum'), self._stream(K)),
+                'rbf_bwd_prep')
+
+  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar):
+    H, C, P, D = zs.shape
+    _f32(theta, 'theta', contiguous=False)
+    self._check(self.lib.vargp_rbf_bwd_finish(
+      _f32(zs, 'zs'), None if Gz1 is None else _f32(Gz1, 'Gz1'), None if Gz2 is None else _f32(Gz2, 'Gz2'),
+      None if Gz1 is None else _f32(r1, 'r1'), None if Gz2 is None else _f32(r2, 'r2'),
+      theta.data_ptr(), theta.stride(0), H, C, P, D, _f32(Z_bar, 'Z_bar'), _f32(theta_bar, 'theta_bar'),
+      self._stream(zs)), 'rbf_bwd_finish')
+
+  def rbf_bwd_xside(self, xs, csum, Gx, theta, theta_bar, x_bar):
+    H, B, D = xs.shape
+    C = 1 if Gx is None else Gx.shape[1]
+    _f32(theta, 'theta', contiguous=False)
+    self._check(self.lib.vargp_rbf_bwd_xside(
+      _f32(xs, 'xs'), _f32(csum, 'csum'), None if Gx is None else _f32(Gx, 'Gx'), theta.data_ptr(), theta.stride(0),
+      H, C, B, D, _f32(theta_bar, 'theta_bar'), None if x_bar is None else _f32(x_bar, 'x_bar'),
+      self._stream(xs)), 'rbf_bwd_xside')
+
+  # -- factorisations -------------------------------------------------------------------------
+  @staticmethod
+  def _mat_batch(t, name):
+    """(.., n, n) tensor whose batch dims collapse to one stride; returns ptr, ld, batch stride, n, batch."""
+    _f32(t, name, contiguous=False)
+    n = t.shape[-1]
+    if t.shape[-2] != n or t.stride(-1) != 1:
+      raise VargpError(f'{name}: expected (..., n, n) with unit inner stride')
+    bshape, bstr = list(t.shape[:-2]), list(t.stride()[:-2])
+    batch = 1
+    for s in bshape:
+      batch *= s
+    bs = 0
+    if batch > 1:
+      # collapse: require stride[i] == stride[i+1] * size[i+1]
+      dims = [(s, st) for s, st in zip(bshape, bstr) if s > 1]
+      for (s0, st0), (s1, st1) in zip(dims[:-1], dims[1:]):
+        if st0 != st1 * s1:
+          raise VargpError(f'{name}: batch dims are not collapsible: shape {bshape} strides {bstr}')
+      bs = dims[-1][1]
+    return t.data_ptr(), t.stride(-2), bs, n, batch
+
+  def chol(self, K, L, jitter, info):
+    ap, ald, abs_, n, batch = self._mat_batch(K, 'K')
+    lp, lld, lbs, n2, batch2 = self._mat_batch(L, 'L')
+    if (n, batch) != (n2, batch2) or info.numel() != batch or info.dtype != torch.int32:
+      raise VargpError('chol: shape mismatch')
+    self._check(self.lib.vargp_chol(ap, ald, abs_, lp, lld, lbs, n, batch, float(jitter), info.data_ptr(),
+                                    self._stream(L)), 'chol')
+
+  def trtri(self, L, W):
+    lp, lld, lbs, n, batch = self._mat_batch(L, 'L')
+    wp, wld, wbs, n2, batch2 = self._mat_batch(W, 'W')
+    if (n, batch) != (n2, batch2):
+      raise VargpError('trtri: shape mismatch')
+    self._check(self.lib.vargp_trtri(lp, lld, lbs, wp, wld, wbs, n, batch, self._stream(W)), 'trtri')
+
+  def tril_unpack(self, vec, out):
+    C, M = out.shape[0], out.shape[-1]
+    if tuple(vec.shape) != (C, M * (M + 1) // 2):
+      raise VargpError('tril_unpack: shape mismatch')
+    self._check(self.lib.vargp_tril_unpack(_f32(vec, 'vec'), C, M, _f32(out, 'out'), self._stream(out)),
+                'tril_unpack')
+
+  def tril_unpack_bwd(self, Lbar, vec, vec_bar):
+    C, M = Lbar.shape[0], Lbar.shape[-1]
+    self._check(self.lib.vargp_tril_unpack_bwd(_f32(Lbar, 'Lbar'), _f32(vec, 'vec'), C, M, _f32(vec_bar, 'vec_bar'),
+                                               self._stream(vec)), 'tril_unpack_bwd')
+
+  # -- KL(u) ----------------------------------------------------------------------------------
+  def kl_fwd(self, W, T, nu, Lu_t, M, kl):
+    H, C, P, _ = W.shape
+    self._check(self.lib.vargp_kl_fwd(_f32(W, 'W'), _f32(T, 'T'), _f32(nu, 'nu'), _f32(Lu_t, 'Lu_t'), H, C, P, M,
+                                      _f32(kl, 'kl'), self._stream(W)), 'kl_fwd')
+
+  def kl_bwd(self, W, T, nu, M, g_kl, Wbar, Tbar, nubar):
+    H, C, P, _ = W.shape
+    self._check(self.lib.vargp_kl_bwd(_f32(W, 'W'), _f32(T, 'T'), _f32(nu, 'nu'), _f32(g_kl, 'g_kl'), H, C, P, M,
+                                      _f32(Wbar, 'Wbar'), _f32(Tbar, 'Tbar'), _f32(nubar, 'nubar'),
+                                      self._stream(W)), 'kl_bwd')
+
+  def kl_bwd_lu(self, Lu_t, g_kl, Lu_bar_t):
+    C, M = Lu_t.shape[0], Lu_t.shape[-1]
+    self._check(self.lib.vargp_kl_bwd_lu(_f32(Lu_t, 'Lu_t'), _f32(g_kl, 'g_kl'), C, M, _f32(Lu_bar_t, 'Lu_bar_t'),
+                                         self._stream(Lu_t)), 'kl_bwd_lu')
+
+  # -- predictive marginal --------------------------------------------------------------------
+  def marginal_reduce(self, V, TV, A, nu, theta, jitter, f_mean, f_var):
+    H, C, P, B = V.shape
+    _f32(theta, 'theta', contiguous=False)
+    self._check(self.lib.vargp_marginal_reduce(
+      _f32(V, 'V'), _f32(TV, 'TV'), _f32(A, 'A'), _f32(nu, 'nu'), theta.data_ptr(), theta.stride(0),
+      theta.shape[1] - 1, H, C, P, B, float(jitter), _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'),
+      self._stream(V)), 'marginal_reduce')
+
+  def marginal_bwd_prep(self, V, TV, A, nu, g_mean, g_var, theta, jitter, Vbar, theta_bar):
+    H, C, P, B = V.shape
+    _f32(theta, 'theta', contiguous=False)
+    self._check(self.lib.vargp_marginal_bwd_prep(
+      _f32(V, 'V'), _f32(TV, 'TV'), _f32(A, 'A'), _f32(nu, 'nu'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'),
+      theta.data_ptr(), theta.stride(0), theta.shape[1] - 1, H, C, P, B, float(jitter), _f32(Vbar, 'Vbar'),
+      _f32(theta_bar, 'theta_bar'), self._stream(V)), 'marginal_bwd_prep')
+
+  def sym_phi(self, X):
+    n = X.shape[-1]
+    self._check(self.lib.vargp_sym_phi(_f32(X, 'X'), n, X.numel() // (n * n), self._stream(X)), 'sym_phi')
+
+  # -- likelihood -----------------------------------------------------------------------------
+  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var):
+    H, F, C, B = eps_f.shape
+    if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous():
+      raise VargpError('nll: y must be a contiguous CUDA int64 tensor')
+    self._check(self.lib.vargp_softmax_nll(
+      _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), y.data_ptr(), H, F, C, B,
+      _f32(nll, 'nll'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'), self._stream(f_mean)), 'softmax_nll')
+
+  def predict(self, f_mean, f_var, eps_f, probs):
+    H, F, C, B = eps_f.shape
+    self._check(self.lib.vargp_softmax_predict(
+      _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), H, F, C, B, _f32(probs, 'probs'),
+      self._stream(f_mean)), 'softmax_predict')
+
+
 _OPS = None
 
 
 def set_ops(o):
+  """Install a kernel interface (used by the CPU tests to inject tests/emu_ops.EmuOps)."""
   global _OPS
   _OPS = o
 
 
 def get_ops():
+  global _OPS
   if _OPS is None:
-    raise RuntimeError('libvargp_sm100.so is not loaded')
+    _OPS = CudaOps()
   return _OPS
