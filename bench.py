@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""ELBO training-step benchmark for the VAR-GP hot path (contract: task prompt section 4 + base contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--task T] [--workload split_mnist|permuted_mnist|scaled]
+    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on the host cores
+
+One "step" mirrors experiments/vargp.py:30-37 of the reference:
+    zero_grad -> kl_h, kl_u, lik = gp.loss(x, y) -> loss = beta*kl_h + kl_u + (N/B)*lik -> backward -> Yogi step.
+Default workload: BASELINE.json configs[1], Split-MNIST shape (C=10 classes, D=784, M=60 inducing points per
+task and class, minibatch 512, H=3 hyper samples, F=10 likelihood samples) at the LAST task (t=4: P=300
+inducing points per class), synthetic data, learned-lengthscale regime.
+
+Prints ONE JSON line (rank 0).  `value` = minibatch ELBO steps per second with inputs resident in HBM,
+aggregated over ranks (weak scaling: every rank steps its own 512-point minibatch, gradients all-reduced);
+`e2e` = the same through the public API from pinned HOST buffers (H2D of x, y and D2H of the three loss
+terms inside the timed region).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+  # name: dict(C, D, M, B, tasks, beta, N)    (experiments/vargp.py:107-109,143-145 defaults)
+  'split_mnist': dict(C=10, D=784, M=60, B=512, tasks=5, beta=10.0, N=10500),
+  'permuted_mnist': dict(C=10, D=784, M=100, B=512, tasks=10, beta=1.64, N=50000),
+  'scaled': dict(C=10, D=784, M=2048, B=65536, tasks=1, beta=1.0, N=1000000),
+}
+H, F = 3, 10
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(hbm=p['hbm_gbs'], bf16=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                src='measured')
+  return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.rows, self.proc, self.index = [], None, index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                    '--format=csv,noheader,nounits', '-lms', '200'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.th = threading.Thread(target=self._read, daemon=True)
+      self.th.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    time.sleep(0.25)
+    self.proc.terminate()
+    self.th.join(timeout=2)
+    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+    return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                reasons=reasons, samples=len(sm))
+
+
+def make_problem(wl, task, device, dtype=torch.float32, seed=0):
+  """Synthetic Split-MNIST-shaped continual-learning state at task `task`."""
+  from vargp_b200.synthetic import make_case
+  cfg = WORKLOADS[wl]
+  params, prev, _, _, _ = make_case(C=cfg['C'], D=cfg['D'], M=cfg['M'], t=task, B=1, H=H, F=F, sigma=10., seed=seed,
+                                    dtype=dtype, with_eps_u=False)
+  return cfg, params, prev
+
+
+def build_gpu_model(params, prev, device):
+  from vargp_b200.vargp import VARGP
+  from vargp_b200.kernels import RBFKernel
+  from vargp_b200.likelihoods import MulticlassSoftmax
+  D = params['z'].size(-1)
+  kern = RBFKernel(D, prior_log_mean=params['prior_log_mean'].clone(), prior_log_logvar=params['prior_log_logvar'].clone())
+  gp = VARGP(params['z'].clone(), kern, MulticlassSoftmax(n_f=F), n_var_samples=H,
+             prev_params=[{k: v.clone() for k, v in p.items()} for p in prev])
+  with torch.no_grad():
+    gp.u_mean.copy_(params['u_mean'])
+    gp.u_tril_vec.copy_(params['u_tril_vec'])
+    gp.kernel.log_mean.copy_(params['log_mean'])
+    gp.kernel.log_logvar.copy_(params['log_logvar'])
+  gp = gp.to(device)
+  gp.sync_errors = False      # no per-step host sync; errors are checked once after the timed region
+  return gp
+
+
+def synth_batches(n, B, D, C, task, device, seed, pin=False):
+  g = torch.Generator().manual_seed(1000 + seed)
+  x = torch.rand(n, B, D, generator=g)
+  y = torch.randint(2 * task, 2 * task + 2, (n, B), generator=g) % C
+  if pin:
+    return x.pin_memory(), y.pin_memory()
+  return x.to(device), y.to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference algorithm (oracle port, op for op) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(wl, task, steps, warmup, budget_s, threads=None):
+  from oracle import vargp_oracle as orc
+  from vargp_b200.optim import Yogi
+  threads = threads or os.cpu_count()
+  torch.set_num_threads(threads)
+  cfg, params, prev = make_problem(wl, task, 'cpu')
+  leaf_keys = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
+  p = {k: (v.clone().requires_grad_(True) if k in leaf_keys else v) for k, v in params.items()}
+  opt = Yogi([p[k] for k in leaf_keys], lr=3e-3)
+  B, D, C = cfg['B'], cfg['D'], cfg['C']
+  xs, ys = synth_batches(4, B, D, C, task, 'cpu', seed=7)
+  Q = task * cfg['M']
+
+  def one(i):
+    opt.zero_grad(set_to_none=True)
+    noise = dict(eps_theta=torch.randn(H, D + 1), eps_f=torch.randn(H, F, C, B))
+    if task > 0:
+      noise['eps_u'] = torch.randn(H, H, C, Q)
+    kl_h, kl_u, nll = orc.elbo_terms(p, prev, xs[i % 4], ys[i % 4], noise, n_v=H)
+    loss = cfg['beta'] * kl_h + kl_u + (cfg['N'] / B) * nll
+    loss.backward()
+    opt.step()
+
+  t0 = time.perf_counter()
+  one(0)
+  t_first = time.perf_counter() - t0
+  for i in range(max(0, warmup - 1)):
+    if (time.perf_counter() - t0) > 0.25 * budget_s:
+      break
+    one(i + 1)
+  steps_eff = max(2, min(steps, int(0.7 * budget_s / max(t_first, 1e-3))))
+  t1 = time.perf_counter()
+  for i in range(steps_eff):
+    one(i)
+  dt = time.perf_counter() - t1
+  return dict(steps=steps_eff, ms_per_step=1e3 * dt / steps_eff, value=steps_eff / dt, cores=threads)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+  import torch.distributed as dist
+  rank = int(os.environ.get('RANK', 0))
+  world = int(os.environ.get('WORLD_SIZE', 1))
+  local = int(os.environ.get('LOCAL_RANK', 0))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  from vargp_b200 import ops as vops
+  from vargp_b200.optim import Yogi
+  from vargp_b200.dist import GradBucket, shard_loss
+
+  wl, task = args.workload, args.task
+  cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
+  gp = build_gpu_model(params, prev, dev)
+  opt = Yogi(gp.parameters(), lr=3e-3)
+  bucket = GradBucket(gp.parameters()) if world > 1 else None
+  ops = vops.get_ops()
+  B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
+  global_B = B * world
+  # minibatch pool larger than the 126 MB L2, rotated every step
+  n_pool = max(4, math.ceil(260e6 / (B * D * 4)))
+  xs, ys = synth_batches(n_pool, B, D, C, task, dev, seed=rank)
+  torch.manual_seed(1234)                               # identical theta draws on every rank
+
+  def step(x, y):
+    opt.zero_grad(set_to_none=True)
+    kl_h, kl_u, nll = gp.loss(x, y)
+    loss = shard_loss(kl_h, kl_u, nll, cfg['beta'], cfg['N'], global_B, world)
+    loss.backward()
+    if bucket is not None:
+      bucket.allreduce()
+    opt.step()
+    return kl_h, kl_u, nll
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+      fn(i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+  K, Wm = args.steps, max(3, args.warmup)
+  for i in range(Wm):
+    step(xs[i % n_pool], ys[i % n_pool])
+  gp.check_errors()
+
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  l0 = ops.launch_count()
+  ms = timed(lambda i: step(xs[i % n_pool], ys[i % n_pool]), K)
+  launches = ops.launch_count() - l0
+  clocks = sampler.stop() if rank == 0 else None
+  gp.check_errors()
+
+  # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the three loss terms ----
+  xh, yh = synth_batches(8, B, D, C, task, dev, seed=100 + rank, pin=True)
+  xd, yd = torch.empty(B, D, device=dev), torch.empty(B, dtype=torch.int64, device=dev)
+  out_h = torch.empty(3, pin_memory=True)
+
+  def e2e_step(i):
+    xd.copy_(xh[i % 8], non_blocking=True)
+    yd.copy_(yh[i % 8], non_blocking=True)
+    kl_h, kl_u, nll = step(xd, yd)
+    out_h.copy_(torch.stack([kl_h.detach(), kl_u.detach(), nll.detach()]), non_blocking=False)
+
+  for i in range(3):
+    e2e_step(i)
+  ms_e2e = timed(e2e_step, K)
+
+  # ---- per-kernel device times (separate instrumented pass, never inside a timed region) ----
+  prof = None
+  if rank == 0:
+    ops.profile_start()
+    nprof = 3
+    for i in range(nprof):
+      step(xs[i % n_pool], ys[i % n_pool])
+    prof = ops.profile_stop()
+    for d in prof.values():
+      for k in ('ms', 'flops', 'bytes'):
+        d[k] /= nprof
+      d['calls'] //= nprof
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    r = cpu_reference_steps(wl if wl != 'scaled' else 'split_mnist', task, 8, 1, budget_s=25.0)
+    cpu = dict(value=r['value'], unit='steps/s', cores=r['cores'], kind='port',
+               sample=f'{r["steps"]} full ELBO steps (fwd+bwd+Yogi) of the same workload on the oracle port '
+                      f'(reference op order incl. its BxB Gram), fp32, {r["cores"]} threads')
+  if world > 1:
+    dist.destroy_process_group()
+  if rank != 0:
+    return
+
+  pk = peaks()
+  by_kernel = {}
+  for tag, d in prof.items():
+    k = by_kernel.setdefault(d['kernel'], dict(ms=0.0, flops=0.0, bytes=0.0, calls=0))
+    for f_ in ('ms', 'flops', 'bytes', 'calls'):
+      k[f_] += d[f_]
+  total_kernel_ms = sum(k['ms'] for k in by_kernel.values())
+  top = max(by_kernel, key=lambda k: by_kernel[k]['ms'])
+  tk = by_kernel[top]
+  if top.startswith('gemm'):
+    tf32x3_peak = pk['bf16_sustained'] / 6.0     # TF32 dense = bf16/2; 3xTF32 issues 3 MMAs per product
+    ach = tk['flops'] / (tk['ms'] * 1e-3) / 1e12
+    roof = dict(kernel=top, bound='tensor', achieved=round(ach, 3), peak=round(tf32x3_peak, 1), unit='TFLOP/s',
+                frac=round(ach / tf32x3_peak, 4), traffic=None,
+                peak_note=f'3xTF32 = {pk["src"]} bf16 sustained / 6', share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
+  else:
+    ach = tk['bytes'] / (tk['ms'] * 1e-3) / 1e9
+    roof = dict(kernel=top, bound='hbm', achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
+                frac=round(ach / pk['hbm'], 4), traffic=None, peak_note=f'{pk["src"]} copy bandwidth',
+                share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
+  value = world * K / (ms * 1e-3)
+  e2e_v = world * K / (ms_e2e * 1e-3)
+  line = {
+    'metric': 'ELBO training steps/s (512-point minibatch steps, summed over ranks)' if wl != 'scaled'
+              else 'ELBO training steps/s (global minibatch sharded over ranks)',
+    'value': round(value if wl != 'scaled' else K / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': world, 'steps': K,
+    'warmup': Wm, 'ms_per_step': round(ms / K, 4), 'higher_is_better': True,
+    'scaling': 'weak' if wl != 'scaled' else 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': {'workload': f'{wl} shape, task t={task}: C={C}, D={D}, M={cfg["M"]}/task, P={(task + 1) * cfg["M"]}, '
+                           f'B={B}/rank, H={H}, F={F}, beta={cfg["beta"]}, Yogi',
+               'l2': f'inputs rotate over a {n_pool * B * D * 4 / 1e6:.0f} MB minibatch pool (> 126 MB L2)',
+               'parallelism': f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL replicated, 1 NCCL all-reduce/step'},
+    'e2e': {'value': round(e2e_v if wl != 'scaled' else K / (ms_e2e * 1e-3), 3), 'unit': 'steps/s',
+            'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 12, 'ms_per_step': round(ms_e2e / K, 4)},
+    'gpu_launches': int(launches),
+    'clocks': clocks,
+    'roofline': roof,
+    'kernels': {k: dict(ms=round(v['ms'], 4), calls=v['calls'],
+                        tflops=round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 3),
+                        gbs=round(v['bytes'] / max(v['ms'], 1e-9) / 1e6, 1)) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms'])},
+    'kernel_ms_per_step': round(total_kernel_ms, 4),
+  }
+  if cpu is not None:
+    line['cpu_baseline'] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in cpu.items()}
+  if args.detail:
+    line['call_sites'] = {t: dict(kernel=d['kernel'], ms=round(d['ms'], 4), calls=d['calls'],
+                                  tflops=round(d['flops'] / max(d['ms'], 1e-9) / 1e9, 3)) for t, d in
+                          sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+  print(json.dumps(line))
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', 0))
+  if rank != 0:
+    return
+  cfg = WORKLOADS[args.workload]
+  wl = args.workload if args.workload != 'scaled' else 'split_mnist'
+  r = cpu_reference_steps(wl, args.task, args.steps, args.warmup, budget_s=170.0)
+  B, C, D = cfg['B'], cfg['C'], cfg['D']
+  line = {
+    'impl': 'reference',
+    'metric': 'ELBO training steps/s (512-point minibatch steps, summed over ranks)',
+    'value': round(r['value'], 4), 'unit': 'steps/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)),
+    'steps': r['steps'], 'warmup': args.warmup, 'ms_per_step': round(r['ms_per_step'], 3), 'higher_is_better': True,
+    'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': {'workload': f'{wl} shape, task t={args.task}: C={C}, D={D}, M={cfg["M"]}/task, '
+                           f'P={(args.task + 1) * cfg["M"]}, B={B}, H={H}, F={F}, beta={cfg["beta"]}, Yogi'},
+    'cpu_baseline': {'value': round(r['value'], 4), 'unit': 'steps/s', 'cores': r['cores'], 'kind': 'port',
+                     'sample': f'{r["steps"]} full ELBO steps (fwd+bwd+Yogi) on the oracle port of the reference '
+                               f'algorithm (reference op order), fp32, {r["cores"]} host threads, rank 0 only'},
+    'e2e': {'value': round(r['value'], 4), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    'gpu_launches': 0,
+  }
+  print(json.dumps(line))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default='split_mnist', choices=sorted(WORKLOADS))
+  ap.add_argument('--task', type=int, default=None)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--detail', action='store_true', help='add per-call-site kernel times to the JSON line')
+  args = ap.parse_args()
+  if args.task is None:
+    args.task = WORKLOADS[args.workload]['tasks'] - 1
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == '__main__':
+  main()

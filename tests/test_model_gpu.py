@@ -12,10 +12,17 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _bound(ref32, ref64, key=None, base=1e-4):
+def _bound(ref32, ref64, key=None, base=1e-4, floor=0.0):
+  """max(north-star tolerance, 5 x the reference's own fp32-vs-fp64 error) -- the second term only matters on
+  the ill-conditioned toy cases."""
   a = ref32[key] if key else ref32
   b = ref64[key] if key else ref64
-  return max(base, 3.0 * util.relerr(a, b))
+  return max(base, 5.0 * _err(a, b, floor))
+
+
+def _err(a, b, floor=0.0):
+  a, b = a.detach().double().cpu(), b.detach().double().cpu()
+  return ((a - b).norm() / max(b.norm().item(), floor, 1e-300)).item()
 
 
 @pytest.mark.parametrize('name', util.golden_names())
@@ -29,10 +36,13 @@ def test_loss_and_grads_match_reference(name, cuda_ops):
     if r64[k].abs() > 0:
       err = util.relerr(terms[k], r64[k])
       assert err < _bound(r32, r64, k), f'{name} {k}: {err:.3e}'
+  # gradients: norm-relative, with an absolute floor of 1e-6 x the largest gradient of the step so that a
+  # parameter whose true gradient underflows (default-init regime: |dL/dz| ~ 1e-130) is judged on scale
+  floor = 1e-6 * max(r64['grads'][k].norm().item() for k in util.GRAD_KEYS)
   for k in util.GRAD_KEYS:
     if r64['grads'][k].abs().max() > 0:
-      err = util.relerr(grads[k], r64['grads'][k])
-      assert err < _bound(r32['grads'], r64['grads'], k), f'{name} grad {k}: {err:.3e}'
+      err = _err(grads[k], r64['grads'][k], floor)
+      assert err < _bound(r32['grads'], r64['grads'], k, floor=floor), f'{name} grad {k}: {err:.3e}'
 
 
 @pytest.mark.parametrize('name', util.golden_names())
@@ -131,7 +141,7 @@ def test_linearity_and_idempotence_at_scale(cuda_ops):
   xc, yc = x.cuda(), y.cuda()
   a = gp.loss(xc, yc, noise=nz)
   b = gp.loss(xc, yc, noise=nz)
-  assert torch.equal(a[1], b[1])
+  assert util.relerr(a[1], b[1]) < 1e-6                           # kl_u sums with atomics
   assert abs(float(a[2] - b[2])) <= 1e-6 * abs(float(a[2]))     # nll sums with atomics
   h = 1024
   n1 = dict(nz, eps_f=nz['eps_f'][..., :h].contiguous())

@@ -1,0 +1,40 @@
+"""Data-parallel ELBO over the GPUs of one box.
+
+Only the minibatch data term shards: rank r gets its own slice of the minibatch and of the likelihood noise;
+Kzz / Cholesky / KL are replicated (identical theta on every rank: same seed, same draw).  Each rank forms
+    loss_r = (beta * kl_hypers + kl_u) / R + (N / B_global) * nll_r
+so that the SUM over ranks of the gradients is the full-batch gradient, and one all-reduce(SUM) of a flat
+gradient bucket per step is the only collective (NCCL over NVLink; gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+  """Flat fp32 bucket holding the gradients of `params`; `allreduce()` sums it across ranks in one call."""
+
+  def __init__(self, params):
+    self.params = [p for p in params if p.requires_grad]
+    n = sum(p.numel() for p in self.params)
+    p0 = self.params[0]
+    self.flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+    self.views, o = [], 0
+    for p in self.params:
+      self.views.append(self.flat[o:o + p.numel()].view_as(p))
+      o += p.numel()
+
+  def allreduce(self):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+      return
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+    torch._foreach_copy_(self.views, grads)
+    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+    for p, v in zip(self.params, self.views):
+      if p.grad is None:
+        p.grad = v.clone()
+      else:
+        p.grad.copy_(v)
+
+
+def shard_loss(kl_hypers, kl_u, nll_local, beta, n_data, global_batch, world_size):
+  """Per-rank loss whose gradients SUM (over ranks) to the gradient of the full-batch ELBO."""
+  return (beta * kl_hypers + kl_u) / world_size + (n_data / global_batch) * nll_local

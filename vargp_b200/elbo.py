@@ -73,8 +73,8 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
 
   # (2) Gram matrices                                                          [kernels.py:45-56]
   Kzz, Kzx = new(H, C, P, P), new(H, C, P, B)
-  ops.rbf_gram(zs4, zn3, zs4, zn3, theta, Kzz, True)
-  ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False)
+  ops.rbf_gram(zs4, zn3, zs4, zn3, theta, Kzz, True, tag='Kzz')
+  ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
 
   # (3) W = chol(Kzz + eps I)^-1                                               [gp_utils.py:5-11]
   L, W = new(H, C, P, P), new(H, C, P, P)
@@ -86,9 +86,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   T, nu = new(H, C, S, M, M), new(H, C, P)
   Wd = _blocks(W, S, M)
   LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M), broadcast over h
-  ops.gemm(Wd, LuB, T, a_tri='lower', b_tri='lower')
+  ops.gemm(Wd, LuB, T, a_tri='lower', b_tri='lower', tag='T=Wss*Lu')
   mB = m_all.permute(1, 0, 2).unsqueeze(0).unsqueeze(-1)        # (1, C, S, M, 1)
-  ops.gemm(Wd, mB, nu.view(H, C, S, M, 1), a_tri='lower')
+  ops.gemm(Wd, mB, nu.view(H, C, S, M, 1), a_tri='lower', tag='nu=Wss*m')
 
   # (5) KL(q(u_t | u_<t) || p(u_t | u_<t))                                     [vargp.py:182-190]
   kl = None
@@ -98,9 +98,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
 
   # (6) predictive marginal                                                    [gp_utils.py:150-191]
   V, TV, A = new(H, C, P, B), new(H, C, P, B), new(H, C, P, B)
-  ops.gemm(W, Kzx, V, a_tri='lower')
-  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper')
-  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper')
+  ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx')
+  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper', tag='TV=Tt*V')
+  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper', tag='A=Wt*V')
   f_mean, f_var = new(H, C, B), new(H, C, B)
   ops.marginal_reduce(V, TV, A, nu, theta, JITTER, f_mean, f_var)
 
@@ -144,29 +144,29 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     # theta_bar[:, D] += 2 gamma^2 sum_cb gv      (direct gamma^2 term of f_var)
     Vbar = new(H, C, P, B)
     ops.marginal_bwd_prep(V, TV, A, nu, g_mean, g_var, theta, JITTER, Vbar, theta_bar)
-    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower')
-    ops.gemm(W, A, Vbar, beta=1., a_tri='lower')
+    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower', tag='Vbar+=T*TVg')
+    ops.gemm(W, A, Vbar, beta=1., a_tri='lower', tag='Vbar+=W*Abar')
     # Kzx_bar = W^T Vbar
     Kxbar = new(H, C, P, B)
-    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper')
+    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar')
     # Wbar = tril(Vbar Kzx^T + V Abar^T)
-    ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower')
-    ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower')
+    ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
+    ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower', tag='Wbar+=V*Abart')
     # Tbar_s = V_s TVg_s^T ; nubar = V gm
-    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar)
-    ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1))
+    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar, tag='Tbar=Vs*TVgt')
+    ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
   if g_kl is not None:
     # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block
     ops.kl_bwd(W, T, nu, M, g_kl, Wbar, Tbar, nubar)
 
   # whitening adjoint: Wbar_ss += tril(Tbar_s Lu_s^T + nubar_s m_s^T); Lu_bar_s = sum_h W_ss^T Tbar_s ; m_bar_s = sum_h W_ss^T nubar_s
   Wbd = _blocks(Wbar, S, M)
-  ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., c_tri='lower')
-  ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower')
+  ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
+  ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
   Lubar_h = new(H, C, S, M, M)
-  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower')
+  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower', tag='whiten_adj')
   mbar_h = new(H, C, S, M, 1)
-  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper')
+  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper', tag='whiten_adj')
   Lu_bar = Lubar_h.sum(0).permute(1, 0, 2, 3).contiguous()      # (S, C, M, M)
   m_bar = mbar_h.sum(0).squeeze(-1).permute(1, 0, 2).contiguous()
   if g_kl is not None:
@@ -175,27 +175,27 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
 
   # Cholesky-inverse adjoint:  Kbar = -W^T Xi W,  Xi = (Phi(X) + Phi(X)^T)/2,  X = tril(Wbar W^T)
   X = new(H, C, P, P)
-  ops.gemm(Wbar, W.transpose(-1, -2), X, a_tri='lower', b_tri='upper', c_tri='lower')
+  ops.gemm(Wbar, W.transpose(-1, -2), X, a_tri='lower', b_tri='upper', c_tri='lower', tag='X=Wbar*Wt')
   ops.sym_phi(X)                                                 # in place -> Xi (full symmetric)
   Y = new(H, C, P, P)
-  ops.gemm(X, W, Y, b_tri='lower')
+  ops.gemm(X, W, Y, b_tri='lower', tag='Y=Xi*W')
   Kzzbar = new(H, C, P, P)
-  ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper')
+  ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper', tag='Kzzbar=-Wt*Y')
 
   # RBF adjoint                                                                 
   r1, r2 = zeros(H, C, P), new(H, C, P)
   csum = zeros(H, B)
   ops.rbf_bwd_prep(Kzzbar, Kzz, r2, None)                       # Kzzbar <- Kzzbar * Kzz ; row sums
   Gz2 = new(H, C, P, D)
-  ops.gemm(Kzzbar, zs, Gz2)
+  ops.gemm(Kzzbar, zs, Gz2, tag='Gz2=Wk2*zs')
   Gz1 = Gx = None
   if have_data:
     ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                      # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
     Gz1 = new(H, C, P, D)
-    ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1)
+    ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
     if need_x_grad:
       Gx = new(H, C, B, D)
-      ops.gemm(Kxbar.transpose(-1, -2), zs, Gx)
+      ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
   Z_bar = new(C, P, D)
   ops.rbf_bwd_finish(zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar)
   x_bar = None

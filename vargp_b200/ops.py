@@ -114,6 +114,54 @@ class CudaOps:
       raise VargpError('vargp_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
     self._inited = set()
     self.use_tc = os.environ.get('VARGP_TC', '1') != '0'
+    self.prof = None              # list of (tag, kernel, flops, bytes, start_event, end_event) when profiling
+
+  # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
+  _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'tril_unpack',
+                 'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'marginal_reduce', 'marginal_bwd_prep',
+                 'sym_phi', 'nll_fwd_bwd', 'predict')
+
+  def profile_start(self):
+    """Bracket every launch with CUDA events (slows the host side; never on during a timed region)."""
+    self.prof = []
+    for name in self._STREAM_OPS:
+      fn = getattr(type(self), name)
+
+      def timed(*a, _fn=fn, _name=name, **kw):
+        # algorithmic bytes of a streaming kernel: every tensor argument is touched once
+        nbytes = sum(t.numel() * t.element_size() for t in a if isinstance(t, torch.Tensor))
+        flops = 0.0
+        if _name in ('chol', 'trtri'):
+          n = a[0].shape[-1]
+          flops = (a[0].numel() // (n * n)) * n ** 3 / 3.0
+        return self._timed(_name, _name, flops, nbytes, lambda: _fn(self, *a, **kw))
+      setattr(self, name, timed)
+
+  def profile_stop(self):
+    """-> {tag: dict(kernel, calls, ms, flops, bytes)} aggregated over the recorded launches."""
+    torch.cuda.synchronize()
+    out = {}
+    for tag, kern, fl, by, e0, e1 in self.prof:
+      d = out.setdefault(tag, dict(kernel=kern, calls=0, ms=0.0, flops=0.0, bytes=0.0))
+      d['calls'] += 1
+      d['ms'] += e0.elapsed_time(e1)
+      d['flops'] += fl
+      d['bytes'] += by
+    self.prof = None
+    for name in self._STREAM_OPS:
+      if name in self.__dict__:
+        delattr(self, name)
+    return out
+
+  def _timed(self, tag, kern, flops, nbytes, fn):
+    if self.prof is None:
+      return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    self.prof.append((tag, kern, float(flops), float(nbytes), e0, e1))
+    return r
 
   # -- plumbing -------------------------------------------------------------------------------
   def _stream(self, t):
@@ -155,21 +203,31 @@ class CudaOps:
     d.epi = EPI_NONE
     return d, nb
 
-  def _run_gemm(self, d, ref):
+  def _run_gemm(self, d, ref, tag):
     s = self._stream(ref)
+    if self.prof is not None:
+      nbat = d.nb[0] * d.nb[1] * d.nb[2]
+      frac = (0.5 if (d.tri_a or d.tri_b) else 1.0) * (0.5 if d.tri_c else 1.0)
+      flops = 2.0 * d.M * d.N * d.K * nbat * frac
+      nbytes = 4.0 * nbat * (d.M * d.K + d.K * d.N + d.M * d.N)
+    else:
+      flops = nbytes = 0.0
     if self.use_tc:
-      rc = self.lib.vargp_gemm_tc(ctypes.byref(d), s)
+      rc = self._timed(tag, 'gemm_tc', flops, nbytes, lambda: self.lib.vargp_gemm_tc(ctypes.byref(d), s))
       if rc == 0:
         return
+      if self.prof is not None:
+        self.prof.pop()
       if rc != -2:
         self._check(rc, 'vargp_gemm_tc')
-    self._check(self.lib.vargp_gemm(ctypes.byref(d), s), 'vargp_gemm')
+    self._check(self._timed(tag, 'gemm_simt', flops, nbytes, lambda: self.lib.vargp_gemm(ctypes.byref(d), s)),
+                'vargp_gemm')
 
-  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None):
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag='gemm'):
     d, _ = self._desc(A, B, C, alpha, beta, a_tri, b_tri, c_tri)
-    self._run_gemm(d, C)
+    self._run_gemm(d, C, tag)
 
-  def rbf_gram(self, a, an, b, bn, theta, out, sym):
+  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram'):
     """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}."""
     _f32(theta, 'theta', contiguous=False)
     d, nb = self._desc(a, b.transpose(-1, -2), out, 1., 0., None, None, None)
@@ -188,7 +246,7 @@ class CudaOps:
     th = theta.as_strided((H,) + (1,) * (out.dim() - 3) + (1, 1), (theta.stride(0),) + (0,) * (out.dim() - 3) + (1, 1))
     d.e_theta_bs = (i64 * 3)(*_bstrides(th, nb))
     d.e_D = theta.shape[1] - 1
-    self._run_gemm(d, out)
+    self._run_gemm(d, out, tag)
 
   # -- RBF operand prep / adjoint -------------------------------------------------------------
   def scale_rows(self, src, theta, dst, norms):

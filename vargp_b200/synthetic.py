@@ -1,0 +1,36 @@
+"""Seed-pinned synthetic VAR-GP problems at the shapes of BASELINE.json: inputs
+x ~ U[0,1]^D (optionally 19 %-sparse like MNIST), previous-task variational parameters, kernel hypers in the
+learned-lengthscale regime.  Pure data generation (CPU torch.Generator streams, stable across machines);
+used by bench.py, the tests and the golden-fixture generator."""
+import math
+
+import torch
+
+
+def make_case(C, D, M, t, B, H=3, F=10, seed=0, sigma=10., dtype=torch.float32, with_eps_u=True,
+              sparse=False, n_v=None):
+  """Seed-pinned synthetic problem.  Everything is drawn in fp64 from one CPU generator and cast, so
+  fp32 and fp64 cases see the same numbers.  H = number of hyper samples actually drawn (1 under
+  map_est), n_v = n_var_samples of the model (defaults to H).  Returns (params, prev, x, y, noise)."""
+  n_v = H if n_v is None else n_v
+  g = torch.Generator().manual_seed(seed)
+  U = lambda *s: torch.rand(*s, generator=g, dtype=torch.float64)
+  Nrm = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+  T = M * (M + 1) // 2
+  prev = [dict(z=U(C, M, D).to(dtype), u_mean=(0.5 * Nrm(C, M, 1)).to(dtype),
+               u_tril_vec=(0.1 * Nrm(C, T)).to(dtype)) for _ in range(t)]
+  log_mean = torch.cat([math.log(sigma) + 0.05 * Nrm(D), torch.full((1,), -0.7, dtype=torch.float64)])
+  params = dict(z=U(C, M, D).to(dtype), u_mean=(0.5 * Nrm(C, M, 1)).to(dtype),
+                u_tril_vec=(0.1 * Nrm(C, T)).to(dtype),
+                log_mean=log_mean.to(dtype), log_logvar=(-2. + 0.1 * Nrm(D + 1)).to(dtype),
+                prior_log_mean=(log_mean + 0.1 * Nrm(D + 1)).to(dtype),
+                prior_log_logvar=(-1.5 + 0.1 * Nrm(D + 1)).to(dtype))
+  x = U(B, D)
+  if sparse:
+    x = x * (U(B, D) < 0.19)
+  x = x.to(dtype)
+  y = torch.randint(0, C, (B,), generator=g)
+  noise = dict(eps_theta=Nrm(H, D + 1).to(dtype), eps_f=Nrm(H, F, C, B).to(dtype))
+  if t > 0 and with_eps_u:
+    noise['eps_u'] = Nrm(n_v, H, C, t * M).to(dtype)
+  return params, prev, x, y, noise
