@@ -69,16 +69,27 @@ class ClockSampler:
     for line in self.proc.stdout:
       self.rows.append([c.strip() for c in line.split(',')])
 
+  def wait_first(self, timeout=5.0):
+    """nvidia-smi takes a while to start: block until its first sample so the timed region is covered."""
+    t0 = time.time()
+    while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+      time.sleep(0.02)
+
+  def mark(self):
+    """Samples from here on belong to the timed region."""
+    self.first = len(self.rows)
+
   def stop(self):
     if self.proc is None:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
     time.sleep(0.25)
     self.proc.terminate()
     self.th.join(timeout=2)
-    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    rows = self.rows[max(0, getattr(self, 'first', 0) - 1):]
+    sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+    mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+    reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in rows)]
     return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
                 reasons=reasons, samples=len(sm))
 
@@ -218,13 +229,19 @@ def run_gpu(args):
     return float(ms)
 
   K, Wm = args.steps, max(3, args.warmup)
-  for i in range(Wm):
-    step(xs[i % n_pool], ys[i % n_pool])
-  gp.check_errors()
-
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
+  for i in range(Wm):
+    step(xs[i % n_pool], ys[i % n_pool])
+  gp.check_errors()
+  if rank == 0:
+    sampler.wait_first()
+  # keep the GPUs under load until the sampler is live, then mark the start of the timed region
+  for i in range(Wm):
+    step(xs[i % n_pool], ys[i % n_pool])
+  if rank == 0:
+    sampler.mark()
   l0 = ops.launch_count()
   ms = timed(lambda i: step(xs[i % n_pool], ys[i % n_pool]), K)
   launches = ops.launch_count() - l0

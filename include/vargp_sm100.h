@@ -118,13 +118,16 @@ int vargp_marginal_bwd_prep(const float* V, float* TV, float* A, const float* nu
 int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream);
 
 /* Kbar *= K (elementwise, in place); rsum[g][i] = row sums; csum[h][j] += sum over (c,i) (optional).
- * Kbar, K are (H, C, Pa, Pb). */
+ * Kbar, K are (H, C, Pa, Pb).  With dsum (symmetric Gram, Pa == Pb) the diagonal products are moved to
+ * dsum[g][i] and zeroed in Kbar / rsum: K_ii = gamma^2 does not depend on z or sigma, so keeping it out of
+ * the z / sigma adjoint avoids an analytic cancellation in fp32. */
 int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_t C, int64_t Pa, int64_t Pb,
-                       float* rsum, float* csum, void* stream);
+                       float* rsum, float* csum, float* dsum, void* stream);
 /* zs_bar = -(r1 + 2 r2) zs + Gz1 + 2 Gz2;  Zbar[c][i][d] = sum_h zs_bar * exp(-theta[h][d]);
- * theta_bar[h][d] += sum_ci (-zs zs_bar - zs Gz1);  theta_bar[h][D] += 2 sum_ci (r1 + r2).  (Gz1, r1) and (Gz2, r2) may each be NULL pairs. */
+ * theta_bar[h][d] += sum_ci (-zs zs_bar - zs Gz1);  theta_bar[h][D] += 2 sum_ci (r1 + r2 + dg).  (Gz1, r1), (Gz2, r2) may each be NULL pairs;
+ * dg (the dsum of vargp_rbf_bwd_prep) may be NULL. */
 int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const float* Gz2, const float* r1, const float* r2,
-                         const float* theta, int64_t theta_rs, int64_t H, int64_t C, int64_t P, int64_t D,
+                         const float* dg, const float* theta, int64_t theta_rs, int64_t H, int64_t C, int64_t P, int64_t D,
                          float* Zbar, float* theta_bar, void* stream);
 /* theta_bar[h][d] += sum_j csum[h][j] xs[h][j][d]^2;  optionally
  * xbar[j][d] = sum_h (-csum xs + sum_c Gx[h][c][j][d]) exp(-theta[h][d])   (Gx, xbar may be NULL) */

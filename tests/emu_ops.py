@@ -88,13 +88,17 @@ class EmuOps:
     d = torch.diag_embed(X.diagonal(dim1=-2, dim2=-1))
     X.copy_(0.5 * (low + low.transpose(-1, -2) + d))
 
-  def rbf_bwd_prep(self, Kbar, K, rsum, csum):
+  def rbf_bwd_prep(self, Kbar, K, rsum, csum, dsum=None):
     Kbar.mul_(K)
+    if dsum is not None:
+      d = Kbar.diagonal(dim1=-2, dim2=-1)
+      dsum.copy_(d)
+      d.zero_()
     rsum.copy_(Kbar.sum(-1))
     if csum is not None:
       csum.add_(Kbar.sum(-2).sum(1))
 
-  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar):
+  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar, dg=None):
     D = zs.shape[-1]
     z0 = torch.zeros_like(zs)
     r1 = torch.zeros_like(zs[..., 0]) if Gz1 is None else r1
@@ -105,6 +109,8 @@ class EmuOps:
     Z_bar.copy_((zsb * torch.exp(-theta[:, :D]).view(-1, 1, 1, D)).sum(0))
     theta_bar[:, :D] += (-zs * zsb - zs * g1).sum((1, 2))
     theta_bar[:, D] += 2. * (r1 + r2).sum((1, 2))
+    if dg is not None:
+      theta_bar[:, D] += 2. * dg.sum((1, 2))
 
   def rbf_bwd_xside(self, xs, csum, Gx, theta, theta_bar, x_bar):
     D = xs.shape[-1]

@@ -231,13 +231,23 @@ def test_rbf_adjoint_kernels(cuda_ops, H, C, P, B, D):
   Kbd, r = dev(Kbar), torch.empty(H, C, P, device='cuda')
   cuda_ops.rbf_bwd_prep(Kbd, dev(K), r, cs)
   close(Kbd, Kb2, 1e-6, 'Wk'); close(r, r64, 1e-5, 'rsum'); close(cs, c64, 1e-5, 'csum')
+  # symmetric variant: diagonal moved out
+  Ks, Ksb = rnd(H, C, P, P, seed=20), rnd(H, C, P, P, seed=21)
+  rs64, ds64 = torch.empty(H, C, P, dtype=torch.float64), torch.empty(H, C, P, dtype=torch.float64)
+  Ksb2 = Ksb.clone()
+  EMU.rbf_bwd_prep(Ksb2, Ks, rs64, None, ds64)
+  Ksbd, rs, ds = dev(Ksb), torch.empty(H, C, P, device='cuda'), torch.empty(H, C, P, device='cuda')
+  cuda_ops.rbf_bwd_prep(Ksbd, dev(Ks), rs, None, ds)
+  close(Ksbd, Ksb2, 1e-6, 'Wk sym'); close(rs, rs64, 1e-5, 'rsum sym'); close(ds, ds64, 1e-6, 'dsum')
+  assert float(Ksbd.diagonal(dim1=-2, dim2=-1).abs().max()) == 0.0
   G1, G2, r1, r2 = rnd(H, C, P, D, seed=7), rnd(H, C, P, D, seed=8), rnd(H, C, P, seed=9), rnd(H, C, P, seed=10)
   for use1, use2 in ((True, True), (False, True), (True, False)):
     Zb64, thb64 = torch.empty(C, P, D, dtype=torch.float64), rnd(H, D + 1, seed=11)
     thb, Zb = dev(thb64), torch.empty(C, P, D, device='cuda')
-    EMU.rbf_bwd_finish(zs, G1 if use1 else None, G2 if use2 else None, r1, r2, theta, Zb64, thb64)
+    dg = rnd(H, C, P, seed=30) if use2 else None
+    EMU.rbf_bwd_finish(zs, G1 if use1 else None, G2 if use2 else None, r1, r2, theta, Zb64, thb64, dg)
     cuda_ops.rbf_bwd_finish(dev(zs), dev(G1) if use1 else None, dev(G2) if use2 else None,
-                            dev(r1), dev(r2), dev(theta), Zb, thb)
+                            dev(r1), dev(r2), dev(theta), Zb, thb, None if dg is None else dev(dg))
     close(Zb, Zb64, 1e-5, 'Zbar'); close(thb, thb64, 1e-5, 'theta_bar finish')
   Gx = rnd(H, C, B, D, seed=12)
   for want_x in (False, True):

@@ -127,8 +127,8 @@ def test_rng_draw_order_matches_reference(cuda_ops):
   a = gp.loss(x.cuda(), y.cuda(), noise=dict(eps_theta=e1, eps_u=e2, eps_f=e3))
   torch.manual_seed(123)
   b = gp.loss(x.cuda(), y.cuda())
-  for u, v in zip(a, b):
-    assert torch.equal(u, v)
+  assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+  assert util.relerr(a[2], b[2]) < 1e-6        # the nll partial sums are combined with float atomics
 
 
 def test_linearity_and_idempotence_at_scale(cuda_ops):

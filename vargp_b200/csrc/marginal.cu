@@ -76,29 +76,33 @@ __global__ void sym_phi_kernel(float* __restrict__ X, int64_t n) {
   x[j * n + i] = v;
 }
 
-// KL(u) forward: one block per (h, c)                                      (vargp.py:182-190)
-__global__ void __launch_bounds__(256)
+// KL(u) forward: ONE block loops over all (h, c) so the sum has a fixed order (bit-reproducible); the work is
+// H*C*M^2 elements (108 k at Split-MNIST shape).                          (vargp.py:182-190)
+__global__ void __launch_bounds__(512)
 kl_fwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
               const float* __restrict__ Lu, int64_t H, int64_t C, int64_t P, int64_t M, float* __restrict__ kl) {
   __shared__ float scratch[32];
-  const int64_t g = blockIdx.x, c = g % C, S = P / M, Q = P - M;
-  const float* w = W + g * P * P;
-  const float* t = T + (g * S + (S - 1)) * M * M;
-  const float* nug = nu + g * P + Q;
-  const float* lu = Lu + c * M * M;
+  const int64_t S = P / M, Q = P - M;
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-    acc -= logf(w[(Q + i) * P + (Q + i)]);
-    acc -= logf(lu[i * M + i]);
-    const float v = nug[i];
-    acc += 0.5f * (v * v - 1.f);
-  }
-  for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const float v = t[e];
-    acc = fmaf(0.5f * v, v, acc);
+  for (int64_t g = 0; g < H * C; ++g) {
+    const int64_t c = g % C;
+    const float* w = W + g * P * P;
+    const float* t = T + (g * S + (S - 1)) * M * M;
+    const float* nug = nu + g * P + Q;
+    const float* lu = Lu + c * M * M;
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+      acc -= logf(w[(Q + i) * P + (Q + i)]);
+      acc -= logf(lu[i * M + i]);
+      const float v = nug[i];
+      acc += 0.5f * (v * v - 1.f);
+    }
+    for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) {
+      const float v = t[e];
+      acc = fmaf(0.5f * v, v, acc);
+    }
   }
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(kl, acc / (float)H);
+  if (threadIdx.x == 0) kl[0] += acc / (float)H;
 }
 
 __global__ void __launch_bounds__(256)
@@ -199,7 +203,7 @@ extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream) {
 extern "C" int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu, int64_t H, int64_t C,
                             int64_t P, int64_t M, float* kl, void* stream) {
   if (!W || !T || !nu || !Lu || !kl || M < 1 || P % M) return VARGP_ERR_ARG;
-  kl_fwd_kernel<<<(unsigned)(H * C), 256, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, H, C, P, M, kl);
+  kl_fwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, H, C, P, M, kl);
   return launch_status();
 }
 

@@ -61,7 +61,7 @@ constexpr int kPrepThreads = 256;
 
 __global__ void __launch_bounds__(kPrepThreads)
 rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64_t C, int64_t Pa, int64_t Pb,
-                    float* __restrict__ rsum, float* __restrict__ csum) {
+                    float* __restrict__ rsum, float* __restrict__ csum, float* __restrict__ dsum) {
   __shared__ float s_red[kPrepRT][kPrepThreads / 32];
   const int64_t g = blockIdx.y;
   const int64_t h = g / C;
@@ -77,7 +77,11 @@ rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64
 #pragma unroll
     for (int r = 0; r < kPrepRT; ++r) {
       if (r < rows) {
-        const float w = kb[(int64_t)r * Pb + j] * kk[(int64_t)r * Pb + j];
+        float w = kb[(int64_t)r * Pb + j] * kk[(int64_t)r * Pb + j];
+        if (dsum && i0 + r == j) {          // symmetric Gram: the diagonal only carries the gamma gradient
+          dsum[g * Pa + j] = w;
+          w = 0.f;
+        }
         kb[(int64_t)r * Pb + j] = w;
         racc[r] += w;
         cacc += w;
@@ -110,7 +114,7 @@ constexpr int kFinThreads = 128;
 
 __global__ void __launch_bounds__(kFinThreads)
 rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz1, const float* __restrict__ Gz2,
-                      const float* __restrict__ r1, const float* __restrict__ r2,
+                      const float* __restrict__ r1, const float* __restrict__ r2, const float* __restrict__ dg,
                       const float* __restrict__ theta, int64_t theta_rs, int64_t H, int64_t R, int64_t D,
                       float* __restrict__ Zbar, float* __restrict__ theta_bar) {
   const int64_t d = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
@@ -145,7 +149,7 @@ rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz
   if (blockIdx.x == 0 && threadIdx.x < rows) {
     for (int64_t h = 0; h < H; ++h) {
       const int64_t row = h * R + row0 + threadIdx.x;
-      atomicAdd(theta_bar + h * (D + 1) + D, 2.f * ((r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f)));
+      atomicAdd(theta_bar + h * (D + 1) + D, 2.f * ((r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f) + (dg ? dg[row] : 0.f)));
     }
   }
 }
@@ -202,23 +206,24 @@ extern "C" int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t 
 }
 
 extern "C" int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_t C, int64_t Pa, int64_t Pb,
-                                  float* rsum, float* csum, void* stream) {
+                                  float* rsum, float* csum, float* dsum, void* stream) {
   if (!Kbar || !K || !rsum || H < 1 || C < 1 || Pa < 1 || Pb < 1) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(Pa, kPrepRT), (unsigned)(H * C));
-  rbf_bwd_prep_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(Kbar, K, C, Pa, Pb, rsum, csum);
+  if (dsum && Pa != Pb) return VARGP_ERR_ARG;
+  rbf_bwd_prep_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(Kbar, K, C, Pa, Pb, rsum, csum, dsum);
   return launch_status();
 }
 
 extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const float* Gz2, const float* r1,
-                                    const float* r2, const float* theta, int64_t theta_rs, int64_t H, int64_t C,
+                                    const float* r2, const float* dg, const float* theta, int64_t theta_rs, int64_t H, int64_t C,
                                     int64_t P, int64_t D, float* Zbar, float* theta_bar, void* stream) {
   if (!zs || !theta || !Zbar || !theta_bar) return VARGP_ERR_ARG;
   if ((Gz1 != nullptr) != (r1 != nullptr) || (Gz2 != nullptr) != (r2 != nullptr)) return VARGP_ERR_ARG;
   const int64_t R = C * P;
   if (ceil_div(R, kFinRows) > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows));
-  rbf_bwd_finish_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(zs, Gz1, Gz2, r1, r2, theta, theta_rs, H, R,
+  rbf_bwd_finish_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs, H, R,
                                                                          D, Zbar, theta_bar);
   return launch_status();
 }

@@ -185,7 +185,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   # RBF adjoint                                                                 
   r1, r2 = zeros(H, C, P), new(H, C, P)
   csum = zeros(H, B)
-  ops.rbf_bwd_prep(Kzzbar, Kzz, r2, None)                       # Kzzbar <- Kzzbar * Kzz ; row sums
+  dg = new(H, C, P)
+  ops.rbf_bwd_prep(Kzzbar, Kzz, r2, None, dg)                   # Kzzbar <- Kzzbar * Kzz (diag -> dg) ; row sums
   Gz2 = new(H, C, P, D)
   ops.gemm(Kzzbar, zs, Gz2, tag='Gz2=Wk2*zs')
   Gz1 = Gx = None
@@ -197,7 +198,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
       Gx = new(H, C, B, D)
       ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
   Z_bar = new(C, P, D)
-  ops.rbf_bwd_finish(zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar)
+  ops.rbf_bwd_finish(zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar, dg)
   x_bar = None
   if have_data:
     x_bar = new(B, D) if need_x_grad else None

@@ -63,11 +63,11 @@ class RbfComputeFn(torch.autograd.Function):
     x_bar = new(C, Pa, D)
     if ctx.sym:
       Wk = (0.5 * (g + g.transpose(-1, -2))).contiguous()     # only the symmetric part of Kbar acts
-      r = new(H, C, Pa)
-      ops.rbf_bwd_prep(Wk, K, r, None)
+      r, dg = new(H, C, Pa), new(H, C, Pa)
+      ops.rbf_bwd_prep(Wk, K, r, None, dg)
       G = new(H, C, Pa, D)
       ops.gemm(Wk, xs, G)
-      ops.rbf_bwd_finish(xs, None, G, None, r, theta, x_bar, theta_bar)
+      ops.rbf_bwd_finish(xs, None, G, None, r, theta, x_bar, theta_bar, dg)
       return theta_bar, x_bar, None, None
     Wk = g.contiguous().clone()
     Cy, Pb = ys.shape[1], ys.shape[2]

@@ -68,8 +68,8 @@ def _load():
   lib.vargp_marginal_bwd_prep.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64,
                                           ctypes.c_float, vp, vp, vp]
   lib.vargp_sym_phi.argtypes = [vp, i64, i64, vp]
-  lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp]
-  lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
+  lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
@@ -263,18 +263,20 @@ class CudaOps:
     self._check(self.lib.vargp_scale_rows(src.data_ptr(), R, D, src.stride(0), theta.data_ptr(), H, theta.stride(0),
                                           _f32(dst, 'dst'), _f32(norms, 'norms'), self._stream(dst)), 'scale_rows')
 
-  def rbf_bwd_prep(self, Kbar, K, rsum, csum):
+  def rbf_bwd_prep(self, Kbar, K, rsum, csum, dsum=None):
     H, C, Pa, Pb = K.shape
     self._check(self.lib.vargp_rbf_bwd_prep(_f32(Kbar, 'Kbar'), _f32(K, 'K'), H, C, Pa, Pb, _f32(rsum, 'rsum'),
-                                            None if csum is None else _f32(csum, 'csum'), self._stream(K)),
+                                            None if csum is None else _f32(csum, 'csum'),
+                                            None if dsum is None else _f32(dsum, 'dsum'), self._stream(K)),
                 'rbf_bwd_prep')
 
-  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar):
+  def rbf_bwd_finish(self, zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar, dg=None):
     H, C, P, D = zs.shape
     _f32(theta, 'theta', contiguous=False)
     self._check(self.lib.vargp_rbf_bwd_finish(
       _f32(zs, 'zs'), None if Gz1 is None else _f32(Gz1, 'Gz1'), None if Gz2 is None else _f32(Gz2, 'Gz2'),
       None if Gz1 is None else _f32(r1, 'r1'), None if Gz2 is None else _f32(r2, 'r2'),
+      None if dg is None else _f32(dg, 'dg'),
       theta.data_ptr(), theta.stride(0), H, C, P, D, _f32(Z_bar, 'Z_bar'), _f32(theta_bar, 'theta_bar'),
       self._stream(zs)), 'rbf_bwd_finish')
 
