@@ -32,7 +32,7 @@ class EmuOps:
       val = torch.where(eye, g2.expand_as(val), val)
     out.copy_(val)
 
-  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag=None):
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag=None, zeroed=False):
     prod = alpha * (_tri(A, a_tri) @ _tri(B, b_tri))
     if c_tri is not None:
       prod = _tri(prod, c_tri)

@@ -1,0 +1,121 @@
+"""tcgen05 / TMA 3xTF32 GEMM (vargp_gemm_tc) against an fp64 product: all operand majors, ragged shapes,
+batch broadcasting, triangular k-skipping, output masks, alpha/beta and the fused RBF epilogue.
+The 3xTF32 split must hold fp32-grade accuracy (norm-relative error < 2e-6)."""
+import math
+
+import pytest
+import torch
+
+from tests.emu_ops import EmuOps
+
+pytestmark = pytest.mark.gpu
+EMU = EmuOps()
+
+
+def rnd(*s, seed=0):
+  g = torch.Generator().manual_seed(seed + sum(s))
+  return torch.randn(*s, generator=g, dtype=torch.float64)
+
+
+def relerr(a, b):
+  a, b = a.double().cpu(), b.double().cpu()
+  return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def make(b, M, N, K, ta, tb):
+  A = rnd(*b, K, M, seed=1).transpose(-1, -2) if ta else rnd(*b, M, K, seed=1)
+  B = rnd(*b, N, K, seed=2).transpose(-1, -2) if tb else rnd(*b, K, N, seed=2)
+  to = lambda t, tr: (t.transpose(-1, -2).contiguous().to('cuda', torch.float32).transpose(-1, -2) if tr
+                      else t.to('cuda', torch.float32))
+  return A, B, to(A, ta), to(B, tb)
+
+
+SHAPES = [(128, 128, 32), (128, 128, 96), (256, 384, 128), (60, 512, 60), (300, 512, 300), (300, 300, 512),
+          (132, 68, 44), (3000, 512, 784), (64, 64, 784), (1000, 1000, 1000)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_tc_gemm_majors(cuda_ops, M, N, K, ta, tb):
+  """(ta, tb) = (False, True): both K-major ("NT"); (False, False): B N-major; (True, False): A M-major, B N-major."""
+  A, B, Ad, Bd = make((2,), M, N, K, ta, tb)
+  C64 = A @ B
+  Cd = torch.full((2, M, N), float('nan'), device='cuda')
+  n0 = cuda_ops.tc_calls
+  cuda_ops.gemm(Ad, Bd, Cd)
+  assert cuda_ops.tc_calls == n0 + 1, 'tensor-core path was not taken'
+  err = relerr(Cd, C64)
+  assert err < 2e-6, f'{(M, N, K, ta, tb)}: {err:.3e}'
+
+
+def test_tc_falls_back_when_unalignable(cuda_ops):
+  A, B, Ad, Bd = make((2,), 130, 70, 45, False, True)      # K = 45: row stride not a multiple of 16 B
+  Cd = torch.empty(2, 130, 70, device='cuda')
+  n0 = cuda_ops.tc_calls
+  cuda_ops.gemm(Ad, Bd, Cd)
+  assert cuda_ops.tc_calls == n0
+  assert relerr(Cd, A @ B) < 2e-6
+
+
+@pytest.mark.parametrize('kw', [
+  dict(a_tri='lower'), dict(a_tri='upper', ta=True), dict(b_tri='lower'), dict(a_tri='lower', b_tri='upper', tb=True, c_tri='lower'),
+  dict(c_tri='lower', beta=1.0, tb=True), dict(c_tri='upper', alpha=-0.5), dict(beta=0.5, alpha=2.0)])
+def test_tc_gemm_flags(cuda_ops, kw):
+  kw = dict(kw)
+  ta, tb = kw.pop('ta', False), kw.pop('tb', False)
+  n = 300
+  A, B, Ad, Bd = make((3, 2), n, n, n, ta, tb)
+  # physically zero the declared triangles (contract of zeroed=True)
+  for t64, td, tri in ((A, Ad, kw.get('a_tri')), (B, Bd, kw.get('b_tri'))):
+    if tri:
+      mask = torch.ones(n, n).tril(-1).bool() if tri == 'upper' else torch.ones(n, n).triu(1).bool()
+      t64.masked_fill_(mask, 0.0)
+      td.masked_fill_(mask.cuda(), 0.0)
+  C0 = rnd(3, 2, n, n, seed=3)
+  C64 = C0.clone()
+  EMU.gemm(A, B, C64, **kw)
+  Cd = C0.to('cuda', torch.float32)
+  n0 = cuda_ops.tc_calls
+  cuda_ops.gemm(Ad, Bd, Cd, zeroed=True, **kw)
+  assert cuda_ops.tc_calls == n0 + 1
+  assert relerr(Cd, C64) < 2e-6, kw
+
+
+def test_tc_batch_broadcast_and_block_views(cuda_ops):
+  H, C, S, M, B = 2, 3, 4, 64, 256
+  P = S * M
+  W = rnd(H, C, P, P, seed=5).tril()
+  V = rnd(H, C, P, B, seed=7)
+  Wd, Vd = W.to('cuda', torch.float32), V.to('cuda', torch.float32)
+  X = rnd(1, 1, B, 96, seed=8)             # broadcast over both batch dims
+  out = torch.empty(H, C, P, 96, device='cuda')
+  n0 = cuda_ops.tc_calls
+  cuda_ops.gemm(Vd, X.to('cuda', torch.float32), out)
+  assert cuda_ops.tc_calls == n0 + 1
+  assert relerr(out, V @ X) < 2e-6
+  # diagonal-block views (3 batch dims, strided blocks)
+  blocks = lambda t: t.as_strided((H, C, S, M, M), (C * P * P, P * P, M * P + M, P, 1))
+  rows = lambda t: t.as_strided((H, C, S, M, B), (C * P * B, P * B, M * B, B, 1))
+  TV64 = torch.empty(H, C, P, B, dtype=torch.float64)
+  EMU.gemm(blocks(W).transpose(-1, -2), rows(V), rows(TV64), a_tri='upper')
+  TVd = torch.empty(H, C, P, B, device='cuda')
+  cuda_ops.gemm(blocks(Wd).transpose(-1, -2), rows(Vd), rows(TVd), a_tri='upper', zeroed=True)
+  assert cuda_ops.tc_calls == n0 + 2
+  assert relerr(TVd, TV64) < 2e-6
+
+
+@pytest.mark.parametrize('H,C,P,B,D', [(3, 10, 300, 512, 784), (2, 3, 64, 100, 64)])
+def test_tc_rbf_epilogue(cuda_ops, H, C, P, B, D):
+  theta = 0.1 * rnd(H, D + 1, seed=1) + math.log(math.sqrt(D) / 3)
+  zs, xs = torch.rand(H, C, P, D, dtype=torch.float64) / 8, torch.rand(H, 1, B, D, dtype=torch.float64) / 8
+  zn, xn = (zs * zs).sum(-1), (xs * xs).sum(-1)
+  K64, Kzz64 = torch.empty(H, C, P, B, dtype=torch.float64), torch.empty(H, C, P, P, dtype=torch.float64)
+  EMU.rbf_gram(zs, zn, xs, xn, theta, K64, False)
+  EMU.rbf_gram(zs, zn, zs, zn, theta, Kzz64, True)
+  f = lambda t: t.to('cuda', torch.float32)
+  Kd, Kzzd = torch.empty(H, C, P, B, device='cuda'), torch.empty(H, C, P, P, device='cuda')
+  n0 = cuda_ops.tc_calls
+  cuda_ops.rbf_gram(f(zs), f(zn), f(xs), f(xn), f(theta), Kd, False)
+  cuda_ops.rbf_gram(f(zs), f(zn), f(zs), f(zn), f(theta), Kzzd, True)
+  assert cuda_ops.tc_calls == n0 + 2
+  assert relerr(Kd, K64) < 3e-6 and relerr(Kzzd, Kzz64) < 3e-6

@@ -10,5 +10,5 @@ if [[ "${1:-}" == "-v" ]]; then EXTRA="-Xptxas -v"; fi
   -Xcompiler -fPIC -shared $EXTRA \
   "$HERE/api.cu" "$HERE/gemm_simt.cu" "$HERE/gemm_tc.cu" "$HERE/rbf.cu" "$HERE/marginal.cu" \
   "$HERE/likelihood.cu" "$HERE/chol.cu" \
-  -lcuda -o "$OUT"
+  -o "$OUT"
 echo "built $OUT"

@@ -1,9 +1,419 @@
-// tcgen05 / TMA 3xTF32 GEMM (placeholder: lands after the SIMT path is parity-green).
+// tcgen05 / TMA batched GEMM with fp32-grade accuracy through 3xTF32 splitting (sm_100a).
+//
+//   C = alpha * A * B (+ beta * C), same descriptor contract as vargp_gemm (gemm_simt.cu), including the
+//   triangular k-range skipping, the lower/upper output mask and the fused RBF epilogue.
+//
+// Pipeline per CTA (one 128 x 128 output tile, K marched in 32-wide slabs, 3 smem stages):
+//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the raw fp32 A / B slabs -> smem
+//   warps 2-5   splitter     : hi = rna.tf32(x) (in place), lo = x - hi (second buffer); fence.proxy.async
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 for lo*hi, hi*lo, hi*hi
+//                              (12 UMMAs of 128x128x8 per slab) into a 128-column fp32 TMEM accumulator;
+//                              tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 6-9   epilogue     : tcgen05.ld (32 lanes x 32 columns at a time) -> alpha/beta/exp epilogue -> global
+// Both operand majors are supported: K-contiguous (K-major UMMA descriptor, one 128 B swizzle atom along K)
+// and M/N-contiguous (MN-major descriptor, four 32-element chunks along M/N, LBO = chunk stride).
+// Structural zeros of triangular operands must be PHYSICALLY zero in memory (TMA cannot mask); callers that
+// only "declare" a triangle stay on the SIMT kernel.
+//
+// Roofline: tensor pipe (3 TF32 MMAs per product); the split doubles the smem footprint of a slab instead of
+// the HBM/L2 traffic.  Algorithmic flops per launch: 2*M*N*K*batch (x 1/2 per triangular flag).
+#include <cuda.h>
+
 #include "common.cuh"
 
-int vargp_tc_init() { return 0; }
+namespace vargp {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per operand slab
+constexpr int TC_THREADS = 320;
+constexpr int TC_SMEM_BYTES = 4 * TC_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_COLS = 128;
+
+struct TcParams {
+  float* C;
+  int64_t M, N, K;
+  int64_t c_rs, c_cs;
+  int64_t nb[3];
+  int64_t c_bs[3];
+  float alpha, beta;
+  int32_t tri_a, tri_b, tri_c, epi;
+  const float* e_row;
+  const float* e_col;
+  int64_t e_row_bs[3], e_col_bs[3];
+  const float* e_theta;
+  int64_t e_theta_bs[3], e_D;
+  int32_t a_mn, b_mn;            // 1: operand is M/N-contiguous (MN-major), 0: K-contiguous
+  int32_t a_b[3], b_b[3];        // 1 if the operand really varies along that batch dim (else coordinate 0)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4) : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // UMMA shared-memory matrix descriptor (SWIZZLE_128B, version 1)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;          // descriptor version (Blackwell)
+  d |= 2ull << 61;          // layout type: SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA_hi = smem;
+  uint8_t* sA_lo = sA_hi + TC_STAGES * TC_TILE_BYTES;
+  uint8_t* sB_hi = sA_lo + TC_STAGES * TC_TILE_BYTES;
+  uint8_t* sB_lo = sB_hi + TC_STAGES * TC_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB_lo + TC_STAGES * TC_TILE_BYTES);
+  uint64_t* full_bar = bars;                      // TMA landed
+  uint64_t* conv_bar = bars + TC_STAGES;          // hi/lo split done
+  uint64_t* empty_bar = bars + 2 * TC_STAGES;     // MMAs that read the stage retired
+  uint64_t* acc_bar = bars + 3 * TC_STAGES;       // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * TC_BM, n0 = (int64_t)blockIdx.x * TC_BN;
+  int64_t z = blockIdx.z;
+  const int i2 = (int)(z % p.nb[2]); z /= p.nb[2];
+  const int i1 = (int)(z % p.nb[1]);
+  const int i0 = (int)(z / p.nb[1]);
+
+  // k-slab range implied by structural zeros / output-triangle culling (warp-uniform)
+  bool dead = false;
+  if (p.tri_c == VARGP_TRI_LOWER && n0 > m0 + TC_BM - 1) dead = true;
+  if (p.tri_c == VARGP_TRI_UPPER && m0 > n0 + TC_BN - 1) dead = true;
+  int64_t k_lo = 0, k_hi = p.K;
+  if (p.tri_a == VARGP_TRI_LOWER) k_hi = min(k_hi, m0 + TC_BM);
+  if (p.tri_a == VARGP_TRI_UPPER) k_lo = max(k_lo, m0);
+  if (p.tri_b == VARGP_TRI_LOWER) k_lo = max(k_lo, n0);
+  if (p.tri_b == VARGP_TRI_UPPER) k_hi = min(k_hi, n0 + TC_BN);
+  const int kb_lo = (int)(k_lo / TC_BK);
+  const int nk = (dead || k_hi <= k_lo) ? 0 : (int)((k_hi + TC_BK - 1) / TC_BK) - kb_lo;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < TC_STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&conv_bar[s], 4);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(acc_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int ca2 = p.a_b[2] ? i2 : 0, ca1 = p.a_b[1] ? i1 : 0, ca0 = p.a_b[0] ? i0 : 0;
+      const int cb2 = p.b_b[2] ? i2 : 0, cb1 = p.b_b[1] ? i1 : 0, cb0 = p.b_b[0] ? i0 : 0;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
+        const int k0 = (kb_lo + it) * TC_BK;
+        uint8_t* da = sA_hi + s * TC_TILE_BYTES;
+        uint8_t* db = sB_hi + s * TC_TILE_BYTES;
+        if (!p.a_mn) {
+          tma_load_5d(&tmA, &full_bar[s], da, k0, (int)m0, ca2, ca1, ca0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_5d(&tmA, &full_bar[s], da + c * 4096, (int)m0 + 32 * c, k0, ca2, ca1, ca0);
+        }
+        if (!p.b_mn) {
+          tma_load_5d(&tmB, &full_bar[s], db, k0, (int)n0, cb2, cb1, cb0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_5d(&tmB, &full_bar[s], db + c * 4096, (int)n0 + 32 * c, k0, cb2, cb1, cb0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % TC_STAGES;
+      const uint32_t ph = (it / TC_STAGES) & 1;
+      mbar_wait(&conv_bar[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(sA_hi + s * TC_TILE_BYTES), a_lo = smem_u32(sA_lo + s * TC_TILE_BYTES);
+        const uint32_t b_hi = smem_u32(sB_hi + s * TC_TILE_BYTES), b_lo = smem_u32(sB_lo + s * TC_TILE_BYTES);
+#pragma unroll
+        for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+          // K-major: 8 tf32 = 32 B further along the 128 B swizzle row.  MN-major: next 8-row k atom (1 KiB).
+          const uint32_t oa = p.a_mn ? k8 * 1024 : k8 * 32;
+          const uint32_t ob = p.b_mn ? k8 * 1024 : k8 * 32;
+          const uint32_t lbo_a = p.a_mn ? 4096 : 16, lbo_b = p.b_mn ? 4096 : 16;
+          const uint64_t dah = make_desc(a_hi + oa, lbo_a, 1024), dal = make_desc(a_lo + oa, lbo_a, 1024);
+          const uint64_t dbh = make_desc(b_hi + ob, lbo_b, 1024), dbl = make_desc(b_lo + ob, lbo_b, 1024);
+          umma_tf32(tmem_base, dal, dbh, idesc, (it > 0 || k8 > 0) ? 1u : 0u);   // small terms first
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);                 // stage reusable once these MMAs retire
+        if (it == nk - 1) umma_commit(acc_bar);     // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ================= hi / lo splitter (128 threads) =================
+    const int t = threadIdx.x - 64;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % TC_STAGES;
+      const uint32_t ph = (it / TC_STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      float4* ah = reinterpret_cast<float4*>(sA_hi + s * TC_TILE_BYTES);
+      float4* al = reinterpret_cast<float4*>(sA_lo + s * TC_TILE_BYTES);
+      float4* bh = reinterpret_cast<float4*>(sB_hi + s * TC_TILE_BYTES);
+      float4* bl = reinterpret_cast<float4*>(sB_lo + s * TC_TILE_BYTES);
+#pragma unroll
+      for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
+        const int idx = e * 128 + t;
+        float4 v = ah[idx], h, l;
+        h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        ah[idx] = h; al[idx] = l;
+        v = bh[idx];
+        h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        bh[idx] = h; bl[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv_bar[s]);
+    }
+  } else {
+    // ================= epilogue (warps 6..9 -> TMEM lane quadrants 2,3,0,1) =================
+    const int quad = warp & 3;
+    const int64_t m = m0 + quad * 32 + lane;
+    float* Cb = p.C + i0 * p.c_bs[0] + i1 * p.c_bs[1] + i2 * p.c_bs[2];
+    float gamma2 = 1.f, rown = 0.f;
+    const float* e_col = nullptr;
+    if (p.epi != VARGP_EPI_NONE) {
+      gamma2 = expf(2.f * p.e_theta[i0 * p.e_theta_bs[0] + i1 * p.e_theta_bs[1] + i2 * p.e_theta_bs[2] + p.e_D]);
+      const float* e_row = p.e_row + i0 * p.e_row_bs[0] + i1 * p.e_row_bs[1] + i2 * p.e_row_bs[2];
+      e_col = p.e_col + i0 * p.e_col_bs[0] + i1 * p.e_col_bs[1] + i2 * p.e_col_bs[2];
+      if (m < p.M) rown = 0.5f * e_row[m];
+    }
+    if (nk > 0) {
+      mbar_wait(acc_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t r[32];
+      if (nk > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (m < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int64_t n = n0 + c * 32 + j;
+          if (n >= p.N) break;
+          const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m);
+          float* cp = Cb + m * p.c_rs + n * p.c_cs;
+          if (masked) {
+            if (p.beta == 0.f) *cp = 0.f;
+            continue;
+          }
+          float v = __uint_as_float(r[j]);
+          if (p.epi != VARGP_EPI_NONE) {
+            v = gamma2 * expf(v - rown - 0.5f * e_col[n]);
+            if (p.epi == VARGP_EPI_RBF_SYM && m == n) v = gamma2;
+          }
+          v *= p.alpha;
+          if (p.beta != 0.f) v = fmaf(p.beta, *cp, v);
+          *cp = v;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static bool g_tc_ready = false;
+
+// operand (rows x K) described by (row stride rs, k stride cs): build a 5-D map (inner, outer, b2, b1, b0)
+static int make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K, int64_t rs, int64_t cs,
+                    const int64_t* nb, const int64_t* bs, bool mn_major, int32_t* use_b) {
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  cuuint32_t box[5] = {32, 1, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (!mn_major) {            // K contiguous: dims (K, rows)
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
+    strides[0] = (cuuint64_t)rs * 4;
+    box[1] = TC_BM;
+  } else {                    // rows (M or N) contiguous: dims (rows, K)
+    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+    strides[0] = (cuuint64_t)cs * 4;
+    box[1] = TC_BK;
+  }
+  for (int i = 0; i < 3; ++i) {            // map dim 2 <- nb[2] (fastest batch), dim 4 <- nb[0]
+    const int b = 2 - i;
+    const bool varies = nb[b] > 1 && bs[b] != 0;
+    use_b[b] = varies ? 1 : 0;
+    dims[2 + i] = varies ? (cuuint64_t)nb[b] : 1;
+    // a unit dim still needs a legal (multiple of 16 B, non-zero) stride
+    strides[1 + i] = varies ? (cuuint64_t)bs[b] * 4 : strides[0] * dims[1];
+  }
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] % 16 != 0 || strides[i] == 0 || strides[i] >= (1ull << 40)) return VARGP_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return VARGP_ERR_UNSUPPORTED;
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : VARGP_ERR_UNSUPPORTED;
+}
+
+}  // namespace vargp
+
+using namespace vargp;
+
+int vargp_tc_init() {
+  if (g_tc_ready) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return e != cudaSuccess ? (int)e : VARGP_ERR_NOT_INIT;
+  g_encode = (EncodeTiledFn)fn;
+  e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  g_tc_ready = true;
+  return 0;
+}
 
 extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
-  (void)g; (void)stream;
-  return VARGP_ERR_UNSUPPORTED;
+  if (!g || !g->A || !g->B || !g->C) return VARGP_ERR_ARG;
+  if (!g_tc_ready) return VARGP_ERR_UNSUPPORTED;
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return VARGP_ERR_UNSUPPORTED;
+  // operand majors
+  const bool a_k = g->a_cs == 1, a_mn = g->a_rs == 1;
+  const bool b_k = g->b_rs == 1, b_mn = g->b_cs == 1;
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return VARGP_ERR_UNSUPPORTED;
+  // too small to pay for the pipeline prologue: leave to the SIMT kernel
+  if (g->M * g->N < 64 * 64 || g->K < 32) return VARGP_ERR_UNSUPPORTED;
+  const int64_t nbatch = g->nb[0] * g->nb[1] * g->nb[2];
+  if (nbatch > 65535 || g->M > (1ll << 30) || g->N > (1ll << 30) || g->K > (1ll << 30)) return VARGP_ERR_UNSUPPORTED;
+
+  TcParams p;
+  p.C = g->C; p.M = g->M; p.N = g->N; p.K = g->K; p.c_rs = g->c_rs; p.c_cs = g->c_cs;
+  for (int i = 0; i < 3; ++i) {
+    p.nb[i] = g->nb[i]; p.c_bs[i] = g->c_bs[i];
+    p.e_row_bs[i] = g->e_row_bs[i]; p.e_col_bs[i] = g->e_col_bs[i]; p.e_theta_bs[i] = g->e_theta_bs[i];
+  }
+  p.alpha = g->alpha; p.beta = g->beta;
+  p.tri_a = g->tri_a; p.tri_b = g->tri_b; p.tri_c = g->tri_c; p.epi = g->epi;
+  p.e_row = g->e_row; p.e_col = g->e_col; p.e_theta = g->e_theta; p.e_D = g->e_D;
+  // prefer the K-major form when a dimension of size 1 makes both strides look contiguous
+  p.a_mn = (a_k && !(a_mn && g->K == 1)) ? 0 : 1;
+  p.b_mn = (b_k && !(b_mn && g->K == 1)) ? 0 : 1;
+
+  alignas(64) CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g->A, g->M, g->K, g->a_rs, g->a_cs, g->nb, g->a_bs, p.a_mn, p.a_b);
+  if (rc) return rc;
+  // B(k, n): "rows" of the operand are n; row stride = b_cs, k stride = b_rs
+  rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b);
+  if (rc) return rc;
+
+  dim3 grid((unsigned)ceil_div(g->N, TC_BN), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return launch_status();
 }

@@ -86,9 +86,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   T, nu = new(H, C, S, M, M), new(H, C, P)
   Wd = _blocks(W, S, M)
   LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M), broadcast over h
-  ops.gemm(Wd, LuB, T, a_tri='lower', b_tri='lower', tag='T=Wss*Lu')
+  ops.gemm(Wd, LuB, T, a_tri='lower', b_tri='lower', tag='T=Wss*Lu', zeroed=True)
   mB = m_all.permute(1, 0, 2).unsqueeze(0).unsqueeze(-1)        # (1, C, S, M, 1)
-  ops.gemm(Wd, mB, nu.view(H, C, S, M, 1), a_tri='lower', tag='nu=Wss*m')
+  ops.gemm(Wd, mB, nu.view(H, C, S, M, 1), a_tri='lower', tag='nu=Wss*m', zeroed=True)
 
   # (5) KL(q(u_t | u_<t) || p(u_t | u_<t))                                     [vargp.py:182-190]
   kl = None
@@ -98,9 +98,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
 
   # (6) predictive marginal                                                    [gp_utils.py:150-191]
   V, TV, A = new(H, C, P, B), new(H, C, P, B), new(H, C, P, B)
-  ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx')
-  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper', tag='TV=Tt*V')
-  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper', tag='A=Wt*V')
+  ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx', zeroed=True)
+  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper', tag='TV=Tt*V', zeroed=True)
+  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper', tag='A=Wt*V', zeroed=True)
   f_mean, f_var = new(H, C, B), new(H, C, B)
   ops.marginal_reduce(V, TV, A, nu, theta, JITTER, f_mean, f_var)
 
@@ -144,11 +144,11 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     # theta_bar[:, D] += 2 gamma^2 sum_cb gv      (direct gamma^2 term of f_var)
     Vbar = new(H, C, P, B)
     ops.marginal_bwd_prep(V, TV, A, nu, g_mean, g_var, theta, JITTER, Vbar, theta_bar)
-    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower', tag='Vbar+=T*TVg')
-    ops.gemm(W, A, Vbar, beta=1., a_tri='lower', tag='Vbar+=W*Abar')
+    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower', tag='Vbar+=T*TVg', zeroed=True)
+    ops.gemm(W, A, Vbar, beta=1., a_tri='lower', tag='Vbar+=W*Abar', zeroed=True)
     # Kzx_bar = W^T Vbar
     Kxbar = new(H, C, P, B)
-    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar')
+    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
     # Wbar = tril(Vbar Kzx^T + V Abar^T)
     ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
     ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower', tag='Wbar+=V*Abart')
@@ -164,9 +164,9 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
   ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
   Lubar_h = new(H, C, S, M, M)
-  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower', tag='whiten_adj')
+  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower', tag='whiten_adj', zeroed=True)
   mbar_h = new(H, C, S, M, 1)
-  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper', tag='whiten_adj')
+  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper', tag='whiten_adj', zeroed=True)
   Lu_bar = Lubar_h.sum(0).permute(1, 0, 2, 3).contiguous()      # (S, C, M, M)
   m_bar = mbar_h.sum(0).squeeze(-1).permute(1, 0, 2).contiguous()
   if g_kl is not None:
@@ -175,12 +175,12 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
 
   # Cholesky-inverse adjoint:  Kbar = -W^T Xi W,  Xi = (Phi(X) + Phi(X)^T)/2,  X = tril(Wbar W^T)
   X = new(H, C, P, P)
-  ops.gemm(Wbar, W.transpose(-1, -2), X, a_tri='lower', b_tri='upper', c_tri='lower', tag='X=Wbar*Wt')
+  ops.gemm(Wbar, W.transpose(-1, -2), X, a_tri='lower', b_tri='upper', c_tri='lower', tag='X=Wbar*Wt', zeroed=True)
   ops.sym_phi(X)                                                 # in place -> Xi (full symmetric)
   Y = new(H, C, P, P)
-  ops.gemm(X, W, Y, b_tri='lower', tag='Y=Xi*W')
+  ops.gemm(X, W, Y, b_tri='lower', tag='Y=Xi*W', zeroed=True)
   Kzzbar = new(H, C, P, P)
-  ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper', tag='Kzzbar=-Wt*Y')
+  ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper', tag='Kzzbar=-Wt*Y', zeroed=True)
 
   # RBF adjoint                                                                 
   r1, r2 = zeros(H, C, P), new(H, C, P)

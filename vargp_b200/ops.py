@@ -115,6 +115,7 @@ class CudaOps:
     self._inited = set()
     self.use_tc = os.environ.get('VARGP_TC', '1') != '0'
     self.prof = None              # list of (tag, kernel, flops, bytes, start_event, end_event) when profiling
+    self.tc_calls = self.simt_calls = 0
 
   # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
   _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'tril_unpack',
@@ -203,7 +204,9 @@ class CudaOps:
     d.epi = EPI_NONE
     return d, nb
 
-  def _run_gemm(self, d, ref, tag):
+  def _run_gemm(self, d, ref, tag, zeroed=False):
+    """tcgen05 path when the problem qualifies (K- or M/N-contiguous operands, TMA-alignable strides) and any
+    declared operand triangle is physically zero (`zeroed`); otherwise the general SIMT kernel."""
     s = self._stream(ref)
     if self.prof is not None:
       nbat = d.nb[0] * d.nb[1] * d.nb[2]
@@ -212,20 +215,24 @@ class CudaOps:
       nbytes = 4.0 * nbat * (d.M * d.K + d.K * d.N + d.M * d.N)
     else:
       flops = nbytes = 0.0
-    if self.use_tc:
+    if self.use_tc and (zeroed or not (d.tri_a or d.tri_b)):
       rc = self._timed(tag, 'gemm_tc', flops, nbytes, lambda: self.lib.vargp_gemm_tc(ctypes.byref(d), s))
       if rc == 0:
+        self.tc_calls += 1
         return
       if self.prof is not None:
         self.prof.pop()
       if rc != -2:
         self._check(rc, 'vargp_gemm_tc')
+    self.simt_calls += 1
     self._check(self._timed(tag, 'gemm_simt', flops, nbytes, lambda: self.lib.vargp_gemm(ctypes.byref(d), s)),
                 'vargp_gemm')
 
-  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag='gemm'):
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag='gemm', zeroed=False):
+    """C = alpha tri_a(A) tri_b(B) [tri_c] + beta C.  `zeroed=True` promises that the other triangle of a
+    declared-triangular operand holds actual zeros (lets the TMA-fed tensor-core kernel take the call)."""
     d, _ = self._desc(A, B, C, alpha, beta, a_tri, b_tri, c_tri)
-    self._run_gemm(d, C, tag)
+    self._run_gemm(d, C, tag, zeroed)
 
   def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram'):
     """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}."""
