@@ -45,7 +45,7 @@ def test_tc_gemm_majors(cuda_ops, M, N, K, ta, tb):
   cuda_ops.gemm(Ad, Bd, Cd)
   assert cuda_ops.tc_calls == n0 + 1, 'tensor-core path was not taken'
   err = relerr(Cd, C64)
-  assert err < 2e-6, f'{(M, N, K, ta, tb)}: {err:.3e}'
+  assert err < 1e-6, f'{(M, N, K, ta, tb)}: {err:.3e}'
 
 
 def test_tc_falls_back_when_unalignable(cuda_ops):
@@ -78,7 +78,7 @@ def test_tc_gemm_flags(cuda_ops, kw):
   n0 = cuda_ops.tc_calls
   cuda_ops.gemm(Ad, Bd, Cd, zeroed=True, **kw)
   assert cuda_ops.tc_calls == n0 + 1
-  assert relerr(Cd, C64) < 2e-6, kw
+  assert relerr(Cd, C64) < 1e-6, kw
 
 
 def test_tc_batch_broadcast_and_block_views(cuda_ops):
@@ -92,7 +92,7 @@ def test_tc_batch_broadcast_and_block_views(cuda_ops):
   n0 = cuda_ops.tc_calls
   cuda_ops.gemm(Vd, X.to('cuda', torch.float32), out)
   assert cuda_ops.tc_calls == n0 + 1
-  assert relerr(out, V @ X) < 2e-6
+  assert relerr(out, V @ X) < 1e-6
   # diagonal-block views (3 batch dims, strided blocks)
   blocks = lambda t: t.as_strided((H, C, S, M, M), (C * P * P, P * P, M * P + M, P, 1))
   rows = lambda t: t.as_strided((H, C, S, M, B), (C * P * B, P * B, M * B, B, 1))
@@ -101,7 +101,7 @@ def test_tc_batch_broadcast_and_block_views(cuda_ops):
   TVd = torch.empty(H, C, P, B, device='cuda')
   cuda_ops.gemm(blocks(Wd).transpose(-1, -2), rows(Vd), rows(TVd), a_tri='upper', zeroed=True)
   assert cuda_ops.tc_calls == n0 + 2
-  assert relerr(TVd, TV64) < 2e-6
+  assert relerr(TVd, TV64) < 1e-6
 
 
 @pytest.mark.parametrize('H,C,P,B,D', [(3, 10, 300, 512, 784), (2, 3, 64, 100, 64)])
@@ -118,4 +118,4 @@ def test_tc_rbf_epilogue(cuda_ops, H, C, P, B, D):
   cuda_ops.rbf_gram(f(zs), f(zn), f(xs), f(xn), f(theta), Kd, False)
   cuda_ops.rbf_gram(f(zs), f(zn), f(zs), f(zn), f(theta), Kzzd, True)
   assert cuda_ops.tc_calls == n0 + 2
-  assert relerr(Kd, K64) < 3e-6 and relerr(Kzzd, Kzz64) < 3e-6
+  assert relerr(Kd, K64) < 1e-6 and relerr(Kzzd, Kzz64) < 1e-6

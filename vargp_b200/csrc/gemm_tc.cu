@@ -7,9 +7,14 @@
 //   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the raw fp32 A / B slabs -> smem
 //   warps 2-5   splitter     : hi = rna.tf32(x) (in place), lo = x - hi (second buffer); fence.proxy.async
 //   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 for lo*hi, hi*lo, hi*hi
-//                              (12 UMMAs of 128x128x8 per slab) into a 128-column fp32 TMEM accumulator;
-//                              tcgen05.commit releases the smem stage / signals the epilogue
-//   warps 6-9   epilogue     : tcgen05.ld (32 lanes x 32 columns at a time) -> alpha/beta/exp epilogue -> global
+//                              (12 UMMAs of 128x128x8 per slab); tcgen05.commit releases the smem stage and
+//                              hands the slab's accumulator to the epilogue
+//   warps 6-13  epilogue     : per slab, tcgen05.ld the hi*hi partial sum and add it in fp32 registers (round to
+//                              nearest); at the end add the lo accumulator, apply alpha/beta/exp, store
+// Accuracy: the tensor core adds into its fp32 accumulator with truncation, which drifts by ~1/4 ulp per MMA
+// step (measured: 2.6e-5 relative on a K=784 Gram with a single accumulator).  Therefore the hi*hi products
+// of each 32-wide slab go to a fresh ping-pong TMEM buffer (4 accumulation steps only) and are promoted to
+// registers, while the 2^-11-times smaller cross terms share one long-running TMEM accumulator.
 // Both operand majors are supported: K-contiguous (K-major UMMA descriptor, one 128 B swizzle atom along K)
 // and M/N-contiguous (MN-major descriptor, four 32-element chunks along M/N, LBO = chunk stride).
 // Structural zeros of triangular operands must be PHYSICALLY zero in memory (TMA cannot mask); callers that
@@ -25,9 +30,10 @@ namespace vargp {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per operand slab
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;                                  // 14 warps: TMA, MMA, 4 split, 8 epilogue
 constexpr int TC_SMEM_BYTES = 4 * TC_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_TMEM_COLS = 512;                                // main0 | main1 | lo | (unused)
 
 struct TcParams {
   float* C;
@@ -81,14 +87,14 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar
       "r"(c3), "r"(c4) : "memory");
 }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // UMMA shared-memory matrix descriptor (SWIZZLE_128B, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
+  // UMMA shared-memory matrix descriptor (version 1); layout 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;          // descriptor version (Blackwell)
-  d |= 2ull << 61;          // layout type: SWIZZLE_128B
+  d |= layout << 61;
   return d;
 }
 
@@ -124,8 +130,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full_bar = bars;                      // TMA landed
   uint64_t* conv_bar = bars + TC_STAGES;          // hi/lo split done
   uint64_t* empty_bar = bars + 2 * TC_STAGES;     // MMAs that read the stage retired
-  uint64_t* acc_bar = bars + 3 * TC_STAGES;       // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+  uint64_t* accf_bar = bars + 3 * TC_STAGES;      // [2] hi*hi partial sum of a slab complete
+  uint64_t* acce_bar = bars + 3 * TC_STAGES + 2;  // [2] partial-sum buffer drained by the epilogue
+  uint64_t* lo_bar = bars + 3 * TC_STAGES + 4;    // cross-term accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.y * TC_BM, n0 = (int64_t)blockIdx.x * TC_BN;
@@ -157,7 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&conv_bar[s], 4);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(acc_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&accf_bar[b], 1);
+        mbar_init(&acce_bar[b], TC_EPI_WARPS);
+      }
+      mbar_init(lo_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -205,25 +217,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int it = 0; it < nk; ++it) {
       const int s = it % TC_STAGES;
       const uint32_t ph = (it / TC_STAGES) & 1;
+      const int buf = it & 1;
       mbar_wait(&conv_bar[s], ph);
+      mbar_wait(&acce_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this partial-sum buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(sA_hi + s * TC_TILE_BYTES), a_lo = smem_u32(sA_lo + s * TC_TILE_BYTES);
         const uint32_t b_hi = smem_u32(sB_hi + s * TC_TILE_BYTES), b_lo = smem_u32(sB_lo + s * TC_TILE_BYTES);
+        const uint32_t t_main = tmem_base + (uint32_t)(buf * TC_BN), t_lo = tmem_base + 2u * TC_BN;
 #pragma unroll
         for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-          // K-major: 8 tf32 = 32 B further along the 128 B swizzle row.  MN-major: next 8-row k atom (1 KiB).
+          // K-major (SWIZZLE_128B): 8 tf32 = 32 B further along the 128 B swizzle row; SBO = 8 rows x 128 B.
+          // MN-major tf32 only exists as SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128 B (SBO = 512 B between
+          // k atoms, LBO = 4 KiB between the 32-element M/N chunks); 8 k per UMMA = 1 KiB further.
           const uint32_t oa = p.a_mn ? k8 * 1024 : k8 * 32;
           const uint32_t ob = p.b_mn ? k8 * 1024 : k8 * 32;
           const uint32_t lbo_a = p.a_mn ? 4096 : 16, lbo_b = p.b_mn ? 4096 : 16;
-          const uint64_t dah = make_desc(a_hi + oa, lbo_a, 1024), dal = make_desc(a_lo + oa, lbo_a, 1024);
-          const uint64_t dbh = make_desc(b_hi + ob, lbo_b, 1024), dbl = make_desc(b_lo + ob, lbo_b, 1024);
-          umma_tf32(tmem_base, dal, dbh, idesc, (it > 0 || k8 > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          const uint32_t sbo_a = p.a_mn ? 512 : 1024, sbo_b = p.b_mn ? 512 : 1024;
+          const uint64_t la = p.a_mn ? 1 : 2, lb = p.b_mn ? 1 : 2;
+          const uint64_t dah = make_desc(a_hi + oa, lbo_a, sbo_a, la), dal = make_desc(a_lo + oa, lbo_a, sbo_a, la);
+          const uint64_t dbh = make_desc(b_hi + ob, lbo_b, sbo_b, lb), dbl = make_desc(b_lo + ob, lbo_b, sbo_b, lb);
+          umma_tf32(t_lo, dal, dbh, idesc, (it > 0 || k8 > 0) ? 1u : 0u);   // cross terms: one long accumulator
+          umma_tf32(t_lo, dah, dbl, idesc, 1u);
+          umma_tf32(t_main, dah, dbh, idesc, k8 > 0 ? 1u : 0u);             // hi*hi: fresh partial sum per slab
         }
-        umma_commit(&empty_bar[s]);                 // stage reusable once these MMAs retire
-        if (it == nk - 1) umma_commit(acc_bar);     // accumulator complete
+        umma_commit(&empty_bar[s]);                 // smem stage reusable once these MMAs retire
+        umma_commit(&accf_bar[buf]);                // slab partial sum ready for promotion
+        if (it == nk - 1) umma_commit(lo_bar);
       }
       __syncwarp();
     }
@@ -255,8 +275,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&conv_bar[s]);
     }
   } else {
-    // ================= epilogue (warps 6..9 -> TMEM lane quadrants 2,3,0,1) =================
+    // ================= epilogue (warps 6..13: TMEM lane quadrant = warp % 4, column half = (warp - 6) / 4) ====
     const int quad = warp & 3;
+    const int half = (warp - 6) >> 2;
     const int64_t m = m0 + quad * 32 + lane;
     float* Cb = p.C + i0 * p.c_bs[0] + i1 * p.c_bs[1] + i2 * p.c_bs[2];
     float gamma2 = 1.f, rown = 0.f;
@@ -267,15 +288,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e_col = p.e_col + i0 * p.e_col_bs[0] + i1 * p.e_col_bs[1] + i2 * p.e_col_bs[2];
       if (m < p.M) rown = 0.5f * e_row[m];
     }
-    if (nk > 0) {
-      mbar_wait(acc_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-#pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t r[32];
-      if (nk > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+    auto drain = [&](uint32_t taddr) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -284,32 +304,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr) : "memory");
+            : "r"(taddr + (uint32_t)(c * 32)) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
       }
-      if (m < p.M) {
+    };
+    for (int it = 0; it < nk; ++it) {
+      const int buf = it & 1;
+      mbar_wait(&accf_bar[buf], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      drain(t_row + (uint32_t)(buf * TC_BN));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acce_bar[buf]);
+    }
+    if (nk > 0) {
+      mbar_wait(lo_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      drain(t_row + 2u * TC_BN);
+    }
+    if (m < p.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int64_t n = n0 + c * 32 + j;
-          if (n >= p.N) break;
-          const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m);
-          float* cp = Cb + m * p.c_rs + n * p.c_cs;
-          if (masked) {
-            if (p.beta == 0.f) *cp = 0.f;
-            continue;
-          }
-          float v = __uint_as_float(r[j]);
-          if (p.epi != VARGP_EPI_NONE) {
-            v = gamma2 * expf(v - rown - 0.5f * e_col[n]);
-            if (p.epi == VARGP_EPI_RBF_SYM && m == n) v = gamma2;
-          }
-          v *= p.alpha;
-          if (p.beta != 0.f) v = fmaf(p.beta, *cp, v);
-          *cp = v;
+      for (int j = 0; j < 64; ++j) {
+        const int64_t n = n0 + half * 64 + j;
+        if (n >= p.N) break;
+        const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m);
+        float* cp = Cb + m * p.c_rs + n * p.c_cs;
+        if (masked) {
+          if (p.beta == 0.f) *cp = 0.f;
+          continue;
         }
+        float v = acc[j];
+        if (p.epi != VARGP_EPI_NONE) {
+          v = gamma2 * expf(v - rown - 0.5f * e_col[n]);
+          if (p.epi == VARGP_EPI_RBF_SYM && m == n) v = gamma2;
+        }
+        v *= p.alpha;
+        if (p.beta != 0.f) v = fmaf(p.beta, *cp, v);
+        *cp = v;
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -358,7 +391,9 @@ static int make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K,
     if (strides[i] % 16 != 0 || strides[i] == 0 || strides[i] >= (1ull << 40)) return VARGP_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return VARGP_ERR_UNSUPPORTED;
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : VARGP_ERR_UNSUPPORTED;
 }
