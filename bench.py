@@ -184,31 +184,23 @@ def run_gpu(args):
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
   from vargp_b200 import ops as vops
-  from vargp_b200.optim import Yogi
-  from vargp_b200.dist import GradBucket, shard_loss
-
   wl, task = args.workload, args.task
   cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
   gp = build_gpu_model(params, prev, dev)
-  opt = Yogi(gp.parameters(), lr=3e-3)
-  bucket = GradBucket(gp.parameters()) if world > 1 else None
   ops = vops.get_ops()
   B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
   global_B = B * world
+  use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
+  from vargp_b200.train import ElboStepper
+  stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
+                        use_graph=use_graph)
   # minibatch pool larger than the 126 MB L2, rotated every step
   n_pool = max(4, math.ceil(260e6 / (B * D * 4)))
   xs, ys = synth_batches(n_pool, B, D, C, task, dev, seed=rank)
   torch.manual_seed(1234)                               # identical theta draws on every rank
 
   def step(x, y):
-    opt.zero_grad(set_to_none=True)
-    kl_h, kl_u, nll = gp.loss(x, y)
-    loss = shard_loss(kl_h, kl_u, nll, cfg['beta'], cfg['N'], global_B, world)
-    loss.backward()
-    if bucket is not None:
-      bucket.allreduce()
-    opt.step()
-    return kl_h, kl_u, nll
+    return stepper.step(x, y)
 
   def barrier():
     if world > 1:
@@ -245,19 +237,18 @@ def run_gpu(args):
   l0 = ops.launch_count()
   ms = timed(lambda i: step(xs[i % n_pool], ys[i % n_pool]), K)
   launches = ops.launch_count() - l0
+  if use_graph:
+    launches = stepper.launches_per_step * K          # replayed from the captured CUDA graph
   clocks = sampler.stop() if rank == 0 else None
   gp.check_errors()
 
   # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the three loss terms ----
   xh, yh = synth_batches(8, B, D, C, task, dev, seed=100 + rank, pin=True)
-  xd, yd = torch.empty(B, D, device=dev), torch.empty(B, dtype=torch.int64, device=dev)
   out_h = torch.empty(3, pin_memory=True)
 
   def e2e_step(i):
-    xd.copy_(xh[i % 8], non_blocking=True)
-    yd.copy_(yh[i % 8], non_blocking=True)
-    kl_h, kl_u, nll = step(xd, yd)
-    out_h.copy_(torch.stack([kl_h.detach(), kl_u.detach(), nll.detach()]), non_blocking=False)
+    kl_h, kl_u, nll = step(xh[i % 8], yh[i % 8])      # H2D from pinned host memory into the step's inputs
+    out_h.copy_(torch.stack([kl_h, kl_u, nll]), non_blocking=False)   # D2H of the loss terms (syncs)
 
   for i in range(3):
     e2e_step(i)
@@ -266,11 +257,13 @@ def run_gpu(args):
   # ---- per-kernel device times (separate instrumented pass, never inside a timed region) ----
   prof = None
   if rank == 0:
+    stepper.use_graph = False                         # eager launches so that each one can be bracketed by events
     ops.profile_start()
     nprof = 3
     for i in range(nprof):
       step(xs[i % n_pool], ys[i % n_pool])
     prof = ops.profile_stop()
+    stepper.use_graph = use_graph
     for d in prof.values():
       for k in ('ms', 'flops', 'bytes'):
         d[k] /= nprof
@@ -318,7 +311,8 @@ def run_gpu(args):
     'config': {'workload': f'{wl} shape, task t={task}: C={C}, D={D}, M={cfg["M"]}/task, P={(task + 1) * cfg["M"]}, '
                            f'B={B}/rank, H={H}, F={F}, beta={cfg["beta"]}, Yogi',
                'l2': f'inputs rotate over a {n_pool * B * D * 4 / 1e6:.0f} MB minibatch pool (> 126 MB L2)',
-               'parallelism': f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL replicated, 1 NCCL all-reduce/step'},
+               'parallelism': f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL replicated, 1 NCCL all-reduce/step',
+               'cuda_graph': bool(use_graph)},
     'e2e': {'value': round(e2e_v if wl != 'scaled' else K / (ms_e2e * 1e-3), 3), 'unit': 'steps/s',
             'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 12, 'ms_per_step': round(ms_e2e / K, 4)},
     'gpu_launches': int(launches),
@@ -372,6 +366,8 @@ def main():
   ap.add_argument('--workload', default='split_mnist', choices=sorted(WORKLOADS))
   ap.add_argument('--task', type=int, default=None)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
+  ap.add_argument('--graph-multi', action='store_true', help='also capture the step (incl. the NCCL all-reduce) when N > 1')
   ap.add_argument('--detail', action='store_true', help='add per-call-site kernel times to the JSON line')
   args = ap.parse_args()
   if args.task is None:

@@ -96,7 +96,7 @@ int vargp_tril_unpack_bwd(const float* Lbar, const float* vec, int64_t C, int64_
 /* kl += (1/H) sum_hc [ -sum_{i in last block} log W_ii - sum_i log Lu_ii + (|T_last|_F^2 + |nu_last|^2 - M)/2 ]
  * W (H,C,P,P), T (H,C,S,M,M), nu (H,C,P), Lu (C,M,M).  Replaces var_gp/vargp.py:182-190. */
 int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu,
-                 int64_t H, int64_t C, int64_t P, int64_t M, float* kl, void* stream);
+                 int64_t H, int64_t C, int64_t P, int64_t M, float* kl, float* work /* H*C floats */, void* stream);
 int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g_kl,
                  int64_t H, int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream);
 int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar, void* stream);
@@ -144,6 +144,13 @@ int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps,
 /* probs[b][c] = (1/HF) sum_hf softmax_C(f)[c]   (var_gp/likelihoods.py:49-63) */
 int vargp_softmax_predict(const float* f_mean, const float* f_var, const float* eps,
                           int64_t H, int64_t F, int64_t C, int64_t B, float* probs, void* stream);
+
+/* Fused Yogi step over a flat parameter buffer (the optimizer the reference trains with,
+ * experiments/vargp.py:23): m <- b1 m + (1-b1) g;  v <- v - (1-b2) sign(v - g^2) g^2;
+ * p <- p - lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps).  pows = {b1^t, b2^t} lives on the device and is
+ * advanced in-stream (initialise to {1, 1}), so the step can be replayed from a CUDA graph. */
+int vargp_yogi_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                    float eps, float* pows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -152,3 +152,12 @@ class EmuOps:
     H, F, C, B = eps_f.shape
     f = f_mean.unsqueeze(1) + f_var.sqrt().unsqueeze(1) * eps_f
     probs.copy_(torch.softmax(f, dim=-2).sum((0, 1)).T / (H * F))
+
+  def yogi_step(self, p, g, m, v, lr, b1, b2, eps, pows):
+    pows[0] *= b1
+    pows[1] *= b2
+    bc1, bc2 = 1. - pows[0], 1. - pows[1]
+    g2 = g * g
+    m.mul_(b1).add_(g, alpha=1. - b1)
+    v.sub_((1. - b2) * torch.sign(v - g2) * g2)
+    p.sub_((lr / bc1) * m / (v.sqrt() / bc2.sqrt() + eps))

@@ -25,6 +25,7 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
             int64_t l_bs, int n, float jitter, int32_t* __restrict__ info) {
   __shared__ __align__(16) float Bs[NB][NB + 4];   // Bs[kk][c] = L[k0 + c][kc + kk]   (transposed block)
   __shared__ __align__(16) float Ds[NB][NB + 4];   // factored diagonal block, Ds[j][l] = Lkk[j][l]
+  __shared__ float Fs[NB][NB + 1];                 // diagonal block during factorisation (conflict-free stride)
   __shared__ float Dinv[NB];
   __shared__ int s_info;
 
@@ -42,7 +43,11 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
       float acc[NB];
       if (live) {
         load_row32(A + (int64_t)(k0 + r) * a_ld + k0, acc, nbk);
-        if (r < NB) acc[r] += jitter;                       // r < nbk here because r < R
+        if (r < NB) {                                       // diagonal entry (static indexing keeps acc in registers)
+#pragma unroll
+          for (int c = 0; c < NB; ++c)
+            if (c == r) acc[c] += jitter;
+        }
       } else {
 #pragma unroll
         for (int c = 0; c < NB; ++c) acc[c] = 0.f;
@@ -72,32 +77,34 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
         }
       }
       if (r0 == 0) {
-        // ---- factor the 32x32 diagonal block in warp 0 (lane i = row i) ----
+        // ---- factor the 32x32 diagonal block in warp 0 (lane i = row i), in shared memory so that the
+        //      column loop can stay a runtime loop (a register-resident version needs dynamic indexing) ----
         if (tid < NB) {
           const int lane = tid;
-          if (lane >= nbk) {                                   // virtual identity rows past the edge
 #pragma unroll
-            for (int c = 0; c < NB; ++c) acc[c] = (c == lane) ? 1.f : 0.f;
-          }
-#pragma unroll
+          for (int c = 0; c < NB; ++c)      // virtual identity rows / columns past the matrix edge
+            Fs[lane][c] = (lane < nbk && c < nbk) ? acc[c] : (c == lane ? 1.f : 0.f);
+          __syncwarp();
           for (int j = 0; j < NB; ++j) {
-            const float d = __shfl_sync(0xffffffffu, acc[j], j);
+            const float d = Fs[j][j];
             if (!(d > 0.f) && lane == 0 && j < nbk && s_info == 0) s_info = k0 + j + 1;
             const float dj = sqrtf(d);
             const float inv = 1.f / dj;
-            if (lane == j) acc[j] = dj;
-            if (lane > j) acc[j] *= inv;
-            const float lij = acc[j];
-#pragma unroll
-            for (int c = j + 1; c < NB; ++c) {
-              const float lcj = __shfl_sync(0xffffffffu, lij, c);
-              if (lane >= c) acc[c] = fmaf(-lij, lcj, acc[c]);
-            }
+            float lij = 0.f;
+            if (lane == j) lij = dj;
+            if (lane > j) lij = Fs[lane][j] * inv;
+            if (lane >= j) Fs[lane][j] = lij;
             if (lane == j) Dinv[j] = inv;
+            __syncwarp();
+            for (int c = j + 1; c < NB; ++c) {
+              const float lcj = Fs[c][j];
+              if (lane >= c) Fs[lane][c] = fmaf(-lij, lcj, Fs[lane][c]);
+            }
+            __syncwarp();
           }
 #pragma unroll
           for (int c = 0; c < NB; ++c) {
-            if (c > lane) acc[c] = 0.f;
+            acc[c] = (c <= lane) ? Fs[lane][c] : 0.f;
             Ds[lane][c] = acc[c];
           }
         }

@@ -146,6 +146,33 @@ gemm_simt_kernel(const vargp_gemm_t g) {
   }
 }
 
+// N == 1 with K-contiguous A: one warp per output row, lanes stride over k (coalesced), shuffle reduce.
+// (nubar = V gm, nu = W_ss m: a 64x64 GEMM tile would waste 63/64 of its lanes.)
+__global__ void __launch_bounds__(256)
+gemv_kernel(const vargp_gemm_t g) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * 8 + wid;
+  int64_t z = blockIdx.z;
+  const int64_t i2 = z % g.nb[2]; z /= g.nb[2];
+  const int64_t i1 = z % g.nb[1];
+  const int64_t i0 = z / g.nb[1];
+  if (m >= g.M) return;
+  const float* __restrict__ A = g.A + i0 * g.a_bs[0] + i1 * g.a_bs[1] + i2 * g.a_bs[2] + m * g.a_rs;
+  const float* __restrict__ B = g.B + i0 * g.b_bs[0] + i1 * g.b_bs[1] + i2 * g.b_bs[2];
+  float* C = g.C + i0 * g.c_bs[0] + i1 * g.c_bs[1] + i2 * g.c_bs[2] + m * g.c_rs;
+  int64_t k_lo = 0, k_hi = g.K;
+  if (g.tri_a == VARGP_TRI_LOWER) k_hi = min(k_hi, m + 1);
+  if (g.tri_a == VARGP_TRI_UPPER) k_lo = m;
+  float acc = 0.f;
+  for (int64_t k = k_lo + lane; k < k_hi; k += 32) acc = fmaf(__ldg(A + k * g.a_cs), __ldg(B + k * g.b_rs), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = g.alpha * acc;
+    if (g.beta != 0.f) v = fmaf(g.beta, *C, v);
+    *C = v;
+  }
+}
+
 static int check_gemm(const vargp_gemm_t* g) {
   if (!g || !g->A || !g->B || !g->C) return VARGP_ERR_ARG;
   if (g->M < 0 || g->N < 0 || g->K < 0) return VARGP_ERR_ARG;
@@ -166,6 +193,12 @@ extern "C" int vargp_gemm(const vargp_gemm_t* g, void* stream) {
   const int64_t nbatch = g->nb[0] * g->nb[1] * g->nb[2];
   if (nbatch > 65535) return VARGP_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
+  if (g->N == 1 && g->epi == VARGP_EPI_NONE && g->tri_b == VARGP_TRI_NONE && g->tri_c == VARGP_TRI_NONE &&
+      g->a_cs <= g->a_rs && g->M >= 8) {
+    dim3 grid((unsigned)ceil_div(g->M, 8), 1, (unsigned)nbatch);
+    gemv_kernel<<<grid, 256, 0, s>>>(*g);
+    return launch_status();
+  }
   // large tiles only when they still fill the machine (148 SMs)
   const int64_t big_tiles = ceil_div(g->M, 128) * ceil_div(g->N, 128) * nbatch;
   if (g->M >= 128 && g->N >= 128 && big_tiles >= 148) {

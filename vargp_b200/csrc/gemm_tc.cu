@@ -424,7 +424,7 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   const bool b_k = g->b_rs == 1, b_mn = g->b_cs == 1;
   if (!(a_k || a_mn) || !(b_k || b_mn)) return VARGP_ERR_UNSUPPORTED;
   // too small to pay for the pipeline prologue: leave to the SIMT kernel
-  if (g->M * g->N < 64 * 64 || g->K < 32) return VARGP_ERR_UNSUPPORTED;
+  if (g->M * g->N < 32 * 32 || g->K < 32) return VARGP_ERR_UNSUPPORTED;
   const int64_t nbatch = g->nb[0] * g->nb[1] * g->nb[2];
   if (nbatch > 65535 || g->M > (1ll << 30) || g->N > (1ll << 30) || g->K > (1ll << 30)) return VARGP_ERR_UNSUPPORTED;
 

@@ -76,32 +76,37 @@ __global__ void sym_phi_kernel(float* __restrict__ X, int64_t n) {
   x[j * n + i] = v;
 }
 
-// KL(u) forward: ONE block loops over all (h, c) so the sum has a fixed order (bit-reproducible); the work is
-// H*C*M^2 elements (108 k at Split-MNIST shape).                          (vargp.py:182-190)
-__global__ void __launch_bounds__(512)
-kl_fwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
-              const float* __restrict__ Lu, int64_t H, int64_t C, int64_t P, int64_t M, float* __restrict__ kl) {
+// KL(u) forward, two deterministic stages (bit-reproducible: no float atomics):
+//   stage 1: one block per (h, c) -> part[g];  stage 2: one warp sums part[] in a fixed order.   (vargp.py:182-190)
+__global__ void __launch_bounds__(256)
+kl_fwd_part_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
+                   const float* __restrict__ Lu, int64_t C, int64_t P, int64_t M, float* __restrict__ part) {
   __shared__ float scratch[32];
-  const int64_t S = P / M, Q = P - M;
+  const int64_t g = blockIdx.x, c = g % C, S = P / M, Q = P - M;
+  const float* w = W + g * P * P;
+  const float* t = T + (g * S + (S - 1)) * M * M;
+  const float* nug = nu + g * P + Q;
+  const float* lu = Lu + c * M * M;
   float acc = 0.f;
-  for (int64_t g = 0; g < H * C; ++g) {
-    const int64_t c = g % C;
-    const float* w = W + g * P * P;
-    const float* t = T + (g * S + (S - 1)) * M * M;
-    const float* nug = nu + g * P + Q;
-    const float* lu = Lu + c * M * M;
-    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-      acc -= logf(w[(Q + i) * P + (Q + i)]);
-      acc -= logf(lu[i * M + i]);
-      const float v = nug[i];
-      acc += 0.5f * (v * v - 1.f);
-    }
-    for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) {
-      const float v = t[e];
-      acc = fmaf(0.5f * v, v, acc);
-    }
+  for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+    acc -= logf(w[(Q + i) * P + (Q + i)]);
+    acc -= logf(lu[i * M + i]);
+    const float v = nug[i];
+    acc += 0.5f * (v * v - 1.f);
+  }
+  for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) {
+    const float v = t[e];
+    acc = fmaf(0.5f * v, v, acc);
   }
   acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) part[g] = acc;
+}
+
+__global__ void __launch_bounds__(32)
+kl_fwd_sum_kernel(const float* __restrict__ part, int64_t G, int64_t H, float* __restrict__ kl) {
+  float acc = 0.f;
+  for (int64_t g = threadIdx.x; g < G; g += 32) acc += part[g];
+  acc = warp_sum(acc);
   if (threadIdx.x == 0) kl[0] += acc / (float)H;
 }
 
@@ -201,9 +206,12 @@ extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream) {
 }
 
 extern "C" int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu, int64_t H, int64_t C,
-                            int64_t P, int64_t M, float* kl, void* stream) {
-  if (!W || !T || !nu || !Lu || !kl || M < 1 || P % M) return VARGP_ERR_ARG;
-  kl_fwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, H, C, P, M, kl);
+                            int64_t P, int64_t M, float* kl, float* work, void* stream) {
+  if (!W || !T || !nu || !Lu || !kl || !work || M < 1 || P % M) return VARGP_ERR_ARG;
+  kl_fwd_part_kernel<<<(unsigned)(H * C), 256, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, C, P, M, work);
+  int rc = launch_status();
+  if (rc) return rc;
+  kl_fwd_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(work, H * C, H, kl);
   return launch_status();
 }
 

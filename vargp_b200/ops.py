@@ -61,7 +61,7 @@ def _load():
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
   lib.vargp_tril_unpack.argtypes = [vp, i64, i64, vp, vp]
   lib.vargp_tril_unpack_bwd.argtypes = [vp, vp, i64, i64, vp, vp]
-  lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp]
+  lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_kl_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_kl_bwd_lu.argtypes = [vp, vp, i64, i64, vp, vp]
   lib.vargp_marginal_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, ctypes.c_float, vp, vp, vp]
@@ -73,6 +73,7 @@ def _load():
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
+  lib.vargp_yogi_step.argtypes = [vp, vp, vp, vp, i64] + [ctypes.c_float] * 4 + [vp, vp]
   return lib
 
 
@@ -120,7 +121,7 @@ class CudaOps:
   # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
   _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'tril_unpack',
                  'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'marginal_reduce', 'marginal_bwd_prep',
-                 'sym_phi', 'nll_fwd_bwd', 'predict')
+                 'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step')
 
   def profile_start(self):
     """Bracket every launch with CUDA events (slows the host side; never on during a timed region)."""
@@ -348,8 +349,9 @@ class CudaOps:
   # -- KL(u) ----------------------------------------------------------------------------------
   def kl_fwd(self, W, T, nu, Lu_t, M, kl):
     H, C, P, _ = W.shape
+    work = torch.empty(H * C, device=W.device, dtype=W.dtype)
     self._check(self.lib.vargp_kl_fwd(_f32(W, 'W'), _f32(T, 'T'), _f32(nu, 'nu'), _f32(Lu_t, 'Lu_t'), H, C, P, M,
-                                      _f32(kl, 'kl'), self._stream(W)), 'kl_fwd')
+                                      _f32(kl, 'kl'), work.data_ptr(), self._stream(W)), 'kl_fwd')
 
   def kl_bwd(self, W, T, nu, M, g_kl, Wbar, Tbar, nubar):
     H, C, P, _ = W.shape
@@ -397,6 +399,13 @@ class CudaOps:
     self._check(self.lib.vargp_softmax_predict(
       _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), H, F, C, B, _f32(probs, 'probs'),
       self._stream(f_mean)), 'softmax_predict')
+
+
+  # -- optimizer ------------------------------------------------------------------------------
+  def yogi_step(self, p, g, m, v, lr, b1, b2, eps, pows):
+    self._check(self.lib.vargp_yogi_step(_f32(p, 'p'), _f32(g, 'g'), _f32(m, 'm'), _f32(v, 'v'), p.numel(),
+                                         float(lr), float(b1), float(b2), float(eps), _f32(pows, 'pows'),
+                                         self._stream(p)), 'yogi_step')
 
 
 _OPS = None

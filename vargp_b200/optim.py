@@ -43,3 +43,43 @@ class Yogi(torch.optim.Optimizer):
       torch._foreach_div_(den, math.sqrt(bc2))
       torch._foreach_add_(den, group['eps'])
       torch._foreach_addcdiv_(ps, ms, den, value=-group['lr'] / bc1)
+
+
+class FlatYogi:
+  """Yogi over ONE flat fp32 buffer, updated by a single fused kernel of libvargp_sm100.so.
+
+  The parameters are re-pointed to views of `flat_p` and their `.grad` to views of `flat_g`, so
+    * `zero_grad()` is one memset and `step()` one launch (CUDA-graph replayable: the bias-correction
+      powers live on the device),
+    * `flat_g` IS the data-parallel gradient bucket: `all_reduce(flat_g)` needs no pack/unpack copies
+      ("backward kernels write straight into the flat bucket").
+  Same update rule and defaults as `Yogi` above (tested against it)."""
+
+  def __init__(self, params, lr=1e-2, betas=(0.9, 0.999), eps=1e-3, initial_accumulator=1e-6):
+    from . import ops as _ops_mod
+    self._ops = _ops_mod.get_ops
+    self.params = [p for p in params if p.requires_grad]
+    self.lr, self.betas, self.eps = lr, betas, eps
+    n = sum(p.numel() for p in self.params)
+    p0 = self.params[0]
+    self.flat_p = torch.empty(n, device=p0.device, dtype=p0.dtype)
+    self.flat_g = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+    self.m = torch.full((n,), initial_accumulator, device=p0.device, dtype=p0.dtype)
+    self.v = torch.full((n,), initial_accumulator, device=p0.device, dtype=p0.dtype)
+    self.pows = torch.ones(2, device=p0.device, dtype=p0.dtype)
+    o = 0
+    with torch.no_grad():
+      for p in self.params:
+        k = p.numel()
+        self.flat_p[o:o + k].copy_(p.reshape(-1))
+        p.data = self.flat_p[o:o + k].view_as(p)
+        p.grad = self.flat_g[o:o + k].view_as(p)
+        o += k
+
+  def zero_grad(self, set_to_none=False):
+    self.flat_g.zero_()
+
+  @torch.no_grad()
+  def step(self):
+    self._ops().yogi_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1],
+                          self.eps, self.pows)
