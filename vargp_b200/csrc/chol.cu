@@ -14,10 +14,31 @@ namespace vargp {
 constexpr int NB = 32;
 constexpr int kCholThreads = 512;
 
-__device__ __forceinline__ void load_row32(const float* p, float (&a)[NB], int valid) {
-  // p points at 32 consecutive floats of one row (not necessarily 16-byte aligned)
+// Thread-per-row kernels need "lane r <- 32 consecutive floats of row r".  Doing that directly costs 32 cache
+// lines per warp request; instead the warp reads row after row fully coalesced (one 128 B line per request)
+// into its private 32 x 33 smem tile and each lane then picks up its own row (stride 33: conflict-free).
+//   base: element (row 0 of the warp's 32-row group, first column); rows_ok rows and cols_ok columns are valid.
+__device__ __forceinline__ void warp_load_rows(const float* base, int64_t ld, int rows_ok, int cols_ok,
+                                               float (*tile)[NB + 1], float (&a)[NB]) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll 8
+  for (int i = 0; i < NB; ++i)
+    tile[i][lane] = (i < rows_ok && lane < cols_ok) ? base[(int64_t)i * ld + lane] : 0.f;
+  __syncwarp();
 #pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = (c < valid) ? p[c] : 0.f;
+  for (int c = 0; c < NB; ++c) a[c] = tile[lane][c];
+}
+__device__ __forceinline__ void warp_store_rows(float* base, int64_t ld, int rows_ok, int cols_ok,
+                                                float (*tile)[NB + 1], const float (&a)[NB]) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NB; ++c) tile[lane][c] = a[c];
+  __syncwarp();
+#pragma unroll 8
+  for (int i = 0; i < NB; ++i)
+    if (i < rows_ok && lane < cols_ok) base[(int64_t)i * ld + lane] = tile[i][lane];
 }
 
 __global__ void __launch_bounds__(kCholThreads)
@@ -25,7 +46,9 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
             int64_t l_bs, int n, float jitter, int32_t* __restrict__ info) {
   __shared__ __align__(16) float Bs[NB][NB + 4];   // Bs[kk][c] = L[k0 + c][kc + kk]   (transposed block)
   __shared__ __align__(16) float Ds[NB][NB + 4];   // factored diagonal block, Ds[j][l] = Lkk[j][l]
-  __shared__ float Fs[NB][NB + 1];                 // diagonal block during factorisation (conflict-free stride)
+  __shared__ __align__(16) float colj[NB];         // column j of the diagonal block during its factorisation
+  extern __shared__ float dyn_tiles[];             // per-warp 32 x 33 transpose tiles
+  float (*tile)[NB + 1] = reinterpret_cast<float (*)[NB + 1]>(dyn_tiles + (threadIdx.x >> 5) * NB * (NB + 1));
   __shared__ float Dinv[NB];
   __shared__ int s_info;
 
@@ -40,17 +63,14 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
     for (int r0 = 0; r0 < R; r0 += kCholThreads) {
       const int r = r0 + tid;
       const bool live = r < R;
+      const int wrow0 = r0 + (tid & ~31);                   // first panel row of this warp's 32-row group
+      const int wrows = min(NB, R - wrow0);                 // <= 0 when the whole warp is past the matrix
       float acc[NB];
-      if (live) {
-        load_row32(A + (int64_t)(k0 + r) * a_ld + k0, acc, nbk);
-        if (r < NB) {                                       // diagonal entry (static indexing keeps acc in registers)
+      warp_load_rows(A + (int64_t)(k0 + wrow0) * a_ld + k0, a_ld, wrows, nbk, tile, acc);
+      if (live && r < NB) {                                 // diagonal entry (static indexing keeps acc in registers)
 #pragma unroll
-          for (int c = 0; c < NB; ++c)
-            if (c == r) acc[c] += jitter;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) acc[c] = 0.f;
+        for (int c = 0; c < NB; ++c)
+          if (c == r) acc[c] += jitter;
       }
       // ---- left-looking update: acc[c] -= sum_{k<k0} L[k0+r][k] * L[k0+c][k] ----
       for (int kc = 0; kc < k0; kc += NB) {
@@ -60,9 +80,9 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
           Bs[kk][c] = (c < nbk) ? L[(int64_t)(k0 + c) * l_ld + kc + kk] : 0.f;
         }
         __syncthreads();
-        if (live) {
+        if (wrows > 0) {
           float a[NB];
-          load_row32(L + (int64_t)(k0 + r) * l_ld + kc, a, NB);
+          warp_load_rows(L + (int64_t)(k0 + wrow0) * l_ld + kc, l_ld, wrows, NB, tile, a);
 #pragma unroll
           for (int kk = 0; kk < NB; ++kk) {
 #pragma unroll
@@ -77,34 +97,45 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
         }
       }
       if (r0 == 0) {
-        // ---- factor the 32x32 diagonal block in warp 0 (lane i = row i), in shared memory so that the
-        //      column loop can stay a runtime loop (a register-resident version needs dynamic indexing) ----
+        // ---- factor the 32x32 diagonal block in warp 0: lane i keeps row i in registers.  The column loop
+        //      is a runtime loop; element j of a row is read / written with fully unrolled selects, so every
+        //      register index is static (dynamic indexing would push the row into local memory).  This block is
+        //      the sequential critical path of the kernel: 15 warps wait for it at the barrier below. ----
         if (tid < NB) {
           const int lane = tid;
+          if (lane >= nbk) {                                   // virtual identity rows past the matrix edge
 #pragma unroll
-          for (int c = 0; c < NB; ++c)      // virtual identity rows / columns past the matrix edge
-            Fs[lane][c] = (lane < nbk && c < nbk) ? acc[c] : (c == lane ? 1.f : 0.f);
-          __syncwarp();
+            for (int c = 0; c < NB; ++c) acc[c] = (c == lane) ? 1.f : 0.f;
+          }
+#pragma unroll 1
           for (int j = 0; j < NB; ++j) {
-            const float d = Fs[j][j];
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) e = (c == j) ? acc[c] : e;
+            const float d = __shfl_sync(0xffffffffu, e, j);
             if (!(d > 0.f) && lane == 0 && j < nbk && s_info == 0) s_info = k0 + j + 1;
             const float dj = sqrtf(d);
             const float inv = 1.f / dj;
-            float lij = 0.f;
-            if (lane == j) lij = dj;
-            if (lane > j) lij = Fs[lane][j] * inv;
-            if (lane >= j) Fs[lane][j] = lij;
+            const float lij = (lane == j) ? dj : ((lane > j) ? e * inv : 0.f);
+            colj[lane] = lij;
             if (lane == j) Dinv[j] = inv;
             __syncwarp();
-            for (int c = j + 1; c < NB; ++c) {
-              const float lcj = Fs[c][j];
-              if (lane >= c) Fs[lane][c] = fmaf(-lij, lcj, Fs[lane][c]);
+#pragma unroll
+            for (int c4 = 0; c4 < NB; c4 += 4) {
+              const float4 l = *reinterpret_cast<const float4*>(&colj[c4]);
+              const float lc[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int c = c4 + u;
+                if (c > j && c <= lane) acc[c] = fmaf(-lij, lc[u], acc[c]);
+                if (c == j) acc[c] = lij;
+              }
             }
             __syncwarp();
           }
 #pragma unroll
           for (int c = 0; c < NB; ++c) {
-            acc[c] = (c <= lane) ? Fs[lane][c] : 0.f;
+            if (c > lane) acc[c] = 0.f;
             Ds[lane][c] = acc[c];
           }
         }
@@ -126,12 +157,7 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
           acc[j] = s * Dinv[j];
         }
       }
-      if (live) {
-        float* lp = L + (int64_t)(k0 + r) * l_ld + k0;
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < nbk) lp[c] = acc[c];
-      }
+      if (wrows > 0) warp_store_rows(L + (int64_t)(k0 + wrow0) * l_ld + k0, l_ld, wrows, nbk, tile, acc);
     }
     // zero the strict upper part to the right of the diagonal block
     const int ncols = n - (k0 + NB);
@@ -146,95 +172,129 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
   if (tid == 0 && info) info[blockIdx.x] = s_info;
 }
 
-// W = L^-1.  Top-down over 32-row blocks; thread j owns column j of the block row being produced:
-// W[k][j] = -Wkk * sum_{l<k} L[k][l] W[l][j], with W[l][j] read coalesced across threads.
-__global__ void __launch_bounds__(kCholThreads)
-trtri_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld,
-             int64_t w_bs, int n) {
-  __shared__ __align__(16) float Lb[NB][NB + 4];   // Lb[kk][c] = L[k0 + c][lc + kk]
-  __shared__ __align__(16) float Ls[NB][NB + 4];   // diagonal block of L
-  __shared__ __align__(16) float Ws[NB][NB + 4];   // its inverse, Ws[c][c'] = Wkk[c][c']
+// W = L^-1 in two kernels.
+//  (1) trtri_diag_kernel: one warp per 32x32 diagonal block: W_kk = L_kk^-1 written into W's diagonal blocks.
+//  (2) trtri_sweep_kernel: the columns of L^-1 are independent, so ONE CTA PER 32-COLUMN BLOCK of every matrix
+//      (grid = column blocks x batch: 300 CTAs at P = 300 instead of 30) walks down its block column:
+//          W[k][j] = -W_kk * sum_{l = j..k-1} L[k][l] W[l][j]            (32x32 blocks)
+//      The 16 warps split the sum over l; lane c owns column c of the block (W read coalesced, the L block
+//      staged per warp in smem and read as broadcasts), partial sums are reduced through shared memory.
+constexpr int kDiagWarps = 4;
 
-  const float* L = Lin + (int64_t)blockIdx.x * l_bs;
-  float* W = Wout + (int64_t)blockIdx.x * w_bs;
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(kDiagWarps * 32)
+trtri_diag_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld, int64_t w_bs, int n,
+                  int nblk) {
+  __shared__ __align__(16) float Ls[kDiagWarps][NB][NB + 4];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x * kDiagWarps + wid;
+  if (blk >= nblk) return;
+  const float* L = Lin + (int64_t)blockIdx.y * l_bs;
+  float* W = Wout + (int64_t)blockIdx.y * w_bs;
+  const int k0 = blk * NB, nbk = min(NB, n - k0);
+  for (int i = 0; i < NB; ++i) {
+    float v = (i == lane) ? 1.f : 0.f;
+    if (i < nbk && lane < nbk && lane <= i) v = L[(int64_t)(k0 + i) * l_ld + k0 + lane];
+    Ls[wid][i][lane] = v;
+  }
+  __syncwarp();
+  // lane j solves L_kk x = e_j by forward substitution; x lives in registers (static indices only)
+  const int j = lane;
+  float x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) x[c] = 0.f;
+#pragma unroll 1
+  for (int i = 0; i < NB; ++i) {
+    float s0 = (i == j) ? 1.f : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < NB; c4 += 4) {
+      const float4 l = *reinterpret_cast<const float4*>(&Ls[wid][i][c4]);
+      s0 = fmaf(-((c4 + 0 < i) ? l.x : 0.f), x[c4 + 0], s0);
+      s1 = fmaf(-((c4 + 1 < i) ? l.y : 0.f), x[c4 + 1], s1);
+      s2 = fmaf(-((c4 + 2 < i) ? l.z : 0.f), x[c4 + 2], s2);
+      s3 = fmaf(-((c4 + 3 < i) ? l.w : 0.f), x[c4 + 3], s3);
+    }
+    const float xi = (i >= j) ? ((s0 + s1) + (s2 + s3)) / Ls[wid][i][i] : 0.f;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = (c == i) ? xi : x[c];
+  }
+  // lane j holds column j; write rows coalesced through the (now free) tile
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NB; ++i) Ls[wid][i][lane] = x[i];
+  __syncwarp();
+  for (int i = 0; i < nbk; ++i)
+    if (lane < nbk) W[(int64_t)(k0 + i) * w_ld + k0 + lane] = (lane <= i) ? Ls[wid][i][lane] : 0.f;
+}
 
-  // zero-fill the strict upper triangle (the block rows below only write j <= row)
-  for (int64_t e = tid; e < (int64_t)n * n; e += kCholThreads) {
-    const int i = (int)(e / n), j = (int)(e % n);
-    if (j > i) W[(int64_t)i * w_ld + j] = 0.f;
+constexpr int kSweepWarps = 16;
+
+__global__ void __launch_bounds__(kSweepWarps * 32)
+trtri_sweep_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld, int64_t w_bs, int n,
+                   int nblk) {
+  extern __shared__ float dyn[];
+  float (*tile)[NB + 1] = reinterpret_cast<float (*)[NB + 1]>(dyn + (threadIdx.x >> 5) * NB * (NB + 1));  // per warp
+  float (*red)[NB][NB + 1] = reinterpret_cast<float (*)[NB][NB + 1]>(dyn + kSweepWarps * NB * (NB + 1));  // [warp][r][c]
+  __shared__ float Ps[NB][NB + 1];
+  __shared__ float Wk[NB][NB + 1];
+
+  const float* L = Lin + (int64_t)blockIdx.y * l_bs;
+  float* W = Wout + (int64_t)blockIdx.y * w_bs;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int jb = blockIdx.x, j0 = jb * NB, ncb = min(NB, n - j0);
+
+  // this CTA owns columns [j0, j0 + ncb): zero everything above its diagonal block
+  for (int e = tid; e < j0 * ncb; e += kSweepWarps * 32) {
+    const int i = e / ncb, c = e % ncb;
+    W[(int64_t)i * w_ld + j0 + c] = 0.f;
   }
 
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nbk = min(NB, n - k0);
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += kCholThreads) {
-      const int i = e / NB, j = e % NB;
-      float v = (i == j) ? 1.f : 0.f;
-      if (i < nbk && j < nbk && j <= i) v = L[(int64_t)(k0 + i) * l_ld + k0 + j];
-      Ls[i][j] = v;
-    }
-    __syncthreads();
-    if (tid < NB) {
-      // lane j solves Lkk x = e_j
-      const int j = tid;
-      float x[NB];
+  for (int kb = jb + 1; kb < nblk; ++kb) {
+    const int k0 = kb * NB, nbk = min(NB, n - k0);
+    __syncthreads();                       // rows written in the previous iteration are visible
+    // ---- partial products: warp w takes l = jb + w, jb + w + 16, ... ----
+    float acc[NB];
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        float s = (i == j) ? 1.f : 0.f;
+    for (int r = 0; r < NB; ++r) acc[r] = 0.f;
+    for (int l = jb + wid; l < kb; l += kSweepWarps) {
+      const int l0 = l * NB;
+      // stage L[kb][l] (rows k0.., cols l0..) coalesced into the warp's tile: tile[r][kk]
+      __syncwarp();
+      for (int r = 0; r < NB; ++r) tile[r][lane] = (r < nbk) ? L[(int64_t)(k0 + r) * l_ld + l0 + lane] : 0.f;
+      float wv[NB];
 #pragma unroll
-        for (int l = 0; l < i; ++l) s = fmaf(-Ls[i][l], x[l], s);
-        x[i] = (i >= j) ? s / Ls[i][i] : 0.f;
+      for (int kk = 0; kk < NB; ++kk) wv[kk] = (lane < ncb) ? W[(int64_t)(l0 + kk) * w_ld + j0 + lane] : 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < NB; ++r) {
+        float a = acc[r];
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) a = fmaf(tile[r][kk], wv[kk], a);     // tile[r][kk]: warp-wide broadcast
+        acc[r] = a;
       }
+    }
 #pragma unroll
-      for (int i = 0; i < NB; ++i) Ws[i][j] = x[i];
+    for (int r = 0; r < NB; ++r) red[wid][r][lane] = acc[r];
+    // W_kk (written by trtri_diag_kernel) -> smem
+    for (int e = tid; e < NB * NB; e += kSweepWarps * 32) {
+      const int r = e / NB, c = e % NB;
+      Wk[r][c] = (r < nbk && c <= r) ? W[(int64_t)(k0 + r) * w_ld + k0 + c] : 0.f;
     }
     __syncthreads();
-    // diagonal block of W
-    for (int e = tid; e < nbk * nbk; e += kCholThreads) {
-      const int i = e / nbk, j = e % nbk;
-      if (j <= i) W[(int64_t)(k0 + i) * w_ld + k0 + j] = Ws[i][j];
+    for (int e = tid; e < NB * NB; e += kSweepWarps * 32) {
+      const int r = e / NB, c = e % NB;
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSweepWarps; ++w) sacc += red[w][r][c];
+      Ps[r][c] = sacc;
     }
-    // off-diagonal part of block row k: columns j < k0
-    for (int j0 = 0; j0 < k0; j0 += kCholThreads) {
-      const int j = j0 + tid;
-      const bool live = j < k0;
-      float acc[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) acc[c] = 0.f;
-      const int lc_begin = (j0 / NB) * NB;          // first chunk any thread of this pass can need
-      for (int lc = lc_begin; lc < k0; lc += NB) {
-        __syncthreads();
-        for (int e = tid; e < NB * NB; e += kCholThreads) {
-          const int c = e / NB, kk = e % NB;
-          Lb[kk][c] = (c < nbk) ? L[(int64_t)(k0 + c) * l_ld + lc + kk] : 0.f;
-        }
-        __syncthreads();
-        if (live && lc + NB > j) {
-#pragma unroll
-          for (int kk = 0; kk < NB; ++kk) {
-            const float w = W[(int64_t)(lc + kk) * w_ld + j];   // zero above the diagonal
-#pragma unroll
-            for (int c4 = 0; c4 < NB; c4 += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(&Lb[kk][c4]);
-              acc[c4 + 0] = fmaf(w, b.x, acc[c4 + 0]);
-              acc[c4 + 1] = fmaf(w, b.y, acc[c4 + 1]);
-              acc[c4 + 2] = fmaf(w, b.z, acc[c4 + 2]);
-              acc[c4 + 3] = fmaf(w, b.w, acc[c4 + 3]);
-            }
-          }
-        }
-      }
-      if (live) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) {
-          if (c < nbk) {
-            float s = 0.f;
-#pragma unroll
-            for (int cp = 0; cp <= c; ++cp) s = fmaf(Ws[c][cp], acc[cp], s);
-            W[(int64_t)(k0 + c) * w_ld + j] = -s;
-          }
-        }
+    __syncthreads();
+    // W[kb][jb] = -W_kk * P
+    for (int e = tid; e < NB * NB; e += kSweepWarps * 32) {
+      const int r = e / NB, c = e % NB;
+      if (r < nbk && c < ncb) {
+        float sacc = 0.f;
+        for (int rp = 0; rp <= r; ++rp) sacc = fmaf(Wk[r][rp], Ps[rp][c], sacc);
+        W[(int64_t)(k0 + r) * w_ld + j0 + c] = -sacc;
       }
     }
   }
@@ -248,8 +308,15 @@ extern "C" int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, 
                           int64_t n, int64_t batch, float jitter, int32_t* info, void* stream) {
   if (!A || !L || n < 1 || batch < 1 || a_ld < n || l_ld < n) return VARGP_ERR_ARG;
   if (n > (1 << 20)) return VARGP_ERR_UNSUPPORTED;
-  chol_kernel<<<(unsigned)batch, kCholThreads, 0, (cudaStream_t)stream>>>(A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
-                                                                          jitter, info);
+  static bool attr_set = false;
+  const int dyn = (kCholThreads / 32) * NB * (NB + 1) * (int)sizeof(float);     // 67.6 KB of transpose tiles
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  chol_kernel<<<(unsigned)batch, kCholThreads, dyn, (cudaStream_t)stream>>>(A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
+                                                                            jitter, info);
   return launch_status();
 }
 
@@ -257,6 +324,21 @@ extern "C" int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W,
                            int64_t n, int64_t batch, void* stream) {
   if (!L || !W || n < 1 || batch < 1 || l_ld < n || w_ld < n) return VARGP_ERR_ARG;
   if (L == W) return VARGP_ERR_ARG;
-  trtri_kernel<<<(unsigned)batch, kCholThreads, 0, (cudaStream_t)stream>>>(L, l_ld, l_bs, W, w_ld, w_bs, (int)n);
+  const int nblk = (int)ceil_div(n, NB);
+  if (batch > 65535) return VARGP_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  trtri_diag_kernel<<<dim3((unsigned)ceil_div(nblk, kDiagWarps), (unsigned)batch), kDiagWarps * 32, 0, s>>>(
+      L, l_ld, l_bs, W, w_ld, w_bs, (int)n, nblk);
+  int rc = launch_status();
+  if (rc) return rc;
+  static bool attr_set = false;
+  const int dyn = (kSweepWarps * NB * (NB + 1) * 2) * (int)sizeof(float);       // per-warp tiles + reduction buffer
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(trtri_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  trtri_sweep_kernel<<<dim3((unsigned)nblk, (unsigned)batch), kSweepWarps * 32, dyn, s>>>(L, l_ld, l_bs, W, w_ld, w_bs,
+                                                                                        (int)n, nblk);
   return launch_status();
 }
