@@ -188,6 +188,8 @@ def run_gpu(args):
   cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
   gp = build_gpu_model(params, prev, dev)
   ops = vops.get_ops()
+  if args.batch:
+    cfg = dict(cfg, B=args.batch)
   B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
   global_B = B * world
   use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
@@ -365,6 +367,7 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='split_mnist', choices=sorted(WORKLOADS))
   ap.add_argument('--task', type=int, default=None)
+  ap.add_argument('--batch', type=int, default=None, help='override the (global) minibatch size of the workload')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
   ap.add_argument('--graph-multi', action='store_true', help='also capture the step (incl. the NCCL all-reduce) when N > 1')

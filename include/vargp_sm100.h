@@ -70,6 +70,11 @@ int vargp_gemm(const vargp_gemm_t* g, void* stream);
 /* tcgen05 / TMA path (3xTF32): same contract as vargp_gemm restricted to K-contiguous operands
  * (a_cs == 1, b_rs == 1), 16-byte aligned rows; returns -2 if the problem does not qualify. */
 int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
+/* vargp_gemm_tc hands problems with at least `min_tiles` 256 x 256 output tiles to the persistent 2-CTA
+ * (cta_group::2) kernel; < 0 disables it, INT64_MIN only queries.  Returns the previous setting.
+ * vargp_tc2_launch_count: launches of that kernel since load. */
+int64_t vargp_tc2_config(int64_t min_tiles);
+int64_t vargp_tc2_launch_count(void);
 
 /* dst[h][r][:] = src[r][:] * exp(-theta[h][:D]);  norms[h][r] = |dst[h][r]|^2.
  * Replaces the `x / sigma` broadcasts and the Gram diagonals of var_gp/kernels.py:41-44,50-51,54. */

@@ -22,98 +22,15 @@
 //
 // Roofline: tensor pipe (3 TF32 MMAs per product); the split doubles the smem footprint of a slab instead of
 // the HBM/L2 traffic.  Algorithmic flops per launch: 2*M*N*K*batch (x 1/2 per triangular flag).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vargp {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KiB per operand slab
+constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 3;
 constexpr int TC_THREADS = 448;                                  // 14 warps: TMA, MMA, 4 split, 8 epilogue
 constexpr int TC_SMEM_BYTES = 4 * TC_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_TMEM_COLS = 512;                                // main0 | main1 | lo | (unused)
-
-struct TcParams {
-  float* C;
-  int64_t M, N, K;
-  int64_t c_rs, c_cs;
-  int64_t nb[3];
-  int64_t c_bs[3];
-  float alpha, beta;
-  int32_t tri_a, tri_b, tri_c, epi;
-  const float* e_row;
-  const float* e_col;
-  int64_t e_row_bs[3], e_col_bs[3];
-  const float* e_theta;
-  int64_t e_theta_bs[3], e_D;
-  int32_t a_mn, b_mn;            // 1: operand is M/N-contiguous (MN-major), 0: K-contiguous
-  int32_t a_b[3], b_b[3];        // 1 if the operand really varies along that batch dim (else coordinate 0)
-};
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra.uni WAIT_DONE;\n\t"
-      "bra.uni WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(a), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3), "r"(c4) : "memory");
-}
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
-  // UMMA shared-memory matrix descriptor (version 1); layout 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;          // descriptor version (Blackwell)
-  d |= layout << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float to_tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -354,49 +271,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-static bool g_tc_ready = false;
+EncodeTiledFn g_encode = nullptr;
+bool g_tc_ready = false;
 
-// operand (rows x K) described by (row stride rs, k stride cs): build a 5-D map (inner, outer, b2, b1, b0)
-static int make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K, int64_t rs, int64_t cs,
-                    const int64_t* nb, const int64_t* bs, bool mn_major, int32_t* use_b) {
-  cuuint64_t dims[5];
-  cuuint64_t strides[4];
-  cuuint32_t box[5] = {32, 1, 1, 1, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  if (!mn_major) {            // K contiguous: dims (K, rows)
-    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
-    strides[0] = (cuuint64_t)rs * 4;
-    box[1] = TC_BM;
-  } else {                    // rows (M or N) contiguous: dims (rows, K)
-    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
-    strides[0] = (cuuint64_t)cs * 4;
-    box[1] = TC_BK;
-  }
-  for (int i = 0; i < 3; ++i) {            // map dim 2 <- nb[2] (fastest batch), dim 4 <- nb[0]
-    const int b = 2 - i;
-    const bool varies = nb[b] > 1 && bs[b] != 0;
-    use_b[b] = varies ? 1 : 0;
-    dims[2 + i] = varies ? (cuuint64_t)nb[b] : 1;
-    // a unit dim still needs a legal (multiple of 16 B, non-zero) stride
-    strides[1 + i] = varies ? (cuuint64_t)bs[b] * 4 : strides[0] * dims[1];
-  }
-  for (int i = 0; i < 4; ++i)
-    if (strides[i] % 16 != 0 || strides[i] == 0 || strides[i] >= (1ull << 40)) return VARGP_ERR_UNSUPPORTED;
-  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return VARGP_ERR_UNSUPPORTED;
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : VARGP_ERR_UNSUPPORTED;
-}
+int tc2_init();                                                                    // gemm_tc2.cu
+int tc2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream);
+bool tc2_wants(const vargp_gemm_t* g);
 
 }  // namespace vargp
 
@@ -411,6 +291,8 @@ int vargp_tc_init() {
   g_encode = (EncodeTiledFn)fn;
   e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
+  int rc = tc2_init();
+  if (rc) return rc;
   g_tc_ready = true;
   return 0;
 }
@@ -447,6 +329,9 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   // B(k, n): "rows" of the operand are n; row stride = b_cs, k stride = b_rs
   rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b);
   if (rc) return rc;
+
+  // large problems: persistent 2-CTA kernel with 256 x 256 tiles (gemm_tc2.cu)
+  if (tc2_wants(g)) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
 
   dim3 grid((unsigned)ceil_div(g->N, TC_BN), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);

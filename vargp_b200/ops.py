@@ -56,6 +56,9 @@ def _load():
   lib.vargp_init.argtypes = [ctypes.c_int]
   lib.vargp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
   lib.vargp_gemm_tc.argtypes = [ctypes.POINTER(GemmDesc), vp]
+  lib.vargp_tc2_config.argtypes = [i64]
+  lib.vargp_tc2_config.restype = i64
+  lib.vargp_tc2_launch_count.restype = i64
   lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
@@ -179,6 +182,13 @@ class CudaOps:
 
   def launch_count(self):
     return int(self.lib.vargp_launch_count())
+
+  def tc2_config(self, min_tiles=None):
+    """Set (or with None query) the tile-count threshold above which GEMMs take the 2-CTA kernel; < 0 disables."""
+    return int(self.lib.vargp_tc2_config(-2 ** 63 if min_tiles is None else int(min_tiles)))
+
+  def tc2_launch_count(self):
+    return int(self.lib.vargp_tc2_launch_count())
 
   # -- GEMM -----------------------------------------------------------------------------------
   def _desc(self, A, B, C, alpha, beta, a_tri, b_tri, c_tri):
