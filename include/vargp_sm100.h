@@ -88,6 +88,13 @@ int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t src_rs,
 int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                int64_t n, int64_t batch, float jitter, int32_t* info, void* stream);
 
+/* Building block of the blocked (GEMM-driven) factorisation of large matrices: same as vargp_chol on one diagonal
+ * block, but a failing pivot is reported as info_base + its 1-based index and, with accumulate != 0, only if
+ * info[b] is still 0 (the first failure of the whole matrix wins). */
+int vargp_chol_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                  int64_t n, int64_t batch, float jitter, int32_t* info, int64_t info_base, int accumulate,
+                  void* stream);
+
 /* W = L^-1 (lower; strict upper zeroed), batched.  Stands in for every torch.triangular_solve of
  * var_gp/gp_utils.py (89,92,124,125,129,134,175,176,182). */
 int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_ld, int64_t w_bs,

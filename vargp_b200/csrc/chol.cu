@@ -43,7 +43,7 @@ __device__ __forceinline__ void warp_store_rows(float* base, int64_t ld, int row
 
 __global__ void __launch_bounds__(kCholThreads)
 chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l_ld,
-            int64_t l_bs, int n, float jitter, int32_t* __restrict__ info) {
+            int64_t l_bs, int n, float jitter, int32_t* __restrict__ info, int info_base, int accumulate) {
   __shared__ __align__(16) float Bs[NB][NB + 4];   // Bs[kk][c] = L[k0 + c][kc + kk]   (transposed block)
   __shared__ __align__(16) float Ds[NB][NB + 4];   // factored diagonal block, Ds[j][l] = Lkk[j][l]
   __shared__ __align__(16) float colj[NB];         // column j of the diagonal block during its factorisation
@@ -169,7 +169,11 @@ chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l
     }
     __syncthreads();
   }
-  if (tid == 0 && info) info[blockIdx.x] = s_info;
+  if (tid == 0 && info) {
+    // blocked drivers factor one diagonal block per call: keep the FIRST failing pivot, in whole-matrix numbering
+    if (!accumulate) info[blockIdx.x] = s_info ? s_info + info_base : 0;
+    else if (s_info && info[blockIdx.x] == 0) info[blockIdx.x] = s_info + info_base;
+  }
 }
 
 // W = L^-1 in two kernels.
@@ -304,8 +308,9 @@ trtri_sweep_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, in
 
 using namespace vargp;
 
-extern "C" int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
-                          int64_t n, int64_t batch, float jitter, int32_t* info, void* stream) {
+extern "C" int vargp_chol_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                             int64_t n, int64_t batch, float jitter, int32_t* info, int64_t info_base, int accumulate,
+                             void* stream) {
   if (!A || !L || n < 1 || batch < 1 || a_ld < n || l_ld < n) return VARGP_ERR_ARG;
   if (n > (1 << 20)) return VARGP_ERR_UNSUPPORTED;
   static bool attr_set = false;
@@ -316,8 +321,13 @@ extern "C" int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, 
     attr_set = true;
   }
   chol_kernel<<<(unsigned)batch, kCholThreads, dyn, (cudaStream_t)stream>>>(A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
-                                                                            jitter, info);
+                                                                            jitter, info, (int)info_base, accumulate);
   return launch_status();
+}
+
+extern "C" int vargp_chol(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                          int64_t n, int64_t batch, float jitter, int32_t* info, void* stream) {
+  return vargp_chol_ex(A, a_ld, a_bs, L, l_ld, l_bs, n, batch, jitter, info, 0, 0, stream);
 }
 
 extern "C" int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_ld, int64_t w_bs,

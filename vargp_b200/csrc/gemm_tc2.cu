@@ -33,8 +33,9 @@ namespace vargp {
 constexpr int T2_STAGES = 3;
 constexpr int T2_THREADS = 512;
 constexpr int T2_BM = 256, T2_BN = 256;                // cluster tile
-constexpr int T2_SMEM_BYTES = 4 * T2_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int T2_EPI_WARPS = 8;                        // per CTA
+constexpr int T2_SMEM_BYTES = 4 * T2_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                              T2_EPI_WARPS * 32 * 33 * 4 /*per-warp transpose tiles of the store*/;
 constexpr int T2_SPLIT_WARPS = 4;                      // per CTA
 constexpr int T2_TMEM_COLS = 512;                      // two 256-column slab accumulators
 
@@ -54,8 +55,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: what crosses the CTA boundary here is never generic-proxy
+// data -- the consumers are tcgen05.mma (async proxy; the writer issues fence.proxy.async first) and TMEM reuse
+// (ordered by tcgen05.fence).  A .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR and was measured as
+// THE bottleneck of this kernel (thousands of cycles per slab on the drain -> MMA hand-back).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -63,7 +68,7 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP_CL:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra.uni WAIT_DONE_CL;\n\t"
       "bra.uni WAIT_LOOP_CL;\n\t"
       "WAIT_DONE_CL:\n\t"
@@ -80,6 +85,20 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t da, uin
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// x -> (hi, lo): hi = x truncated to tf32 (what the tensor core sees when it is fed x itself), lo = x - hi rounded to
+// tf32 (round-half-up on the magnitude, 2 integer ops: left to the hardware, lo would be TRUNCATED, a one-sided error)
+__device__ __forceinline__ float tf32_lo_of(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -142,7 +161,7 @@ __device__ __forceinline__ T2Tile t2_tile(const TcParams& p, const T2Sched& sc, 
 template <bool T2_RAW_HI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-                const int c_vec4) {
+                const int c_vec4, const int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA_hi = smem;
@@ -156,6 +175,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* accf_bar = bars + 3 * T2_STAGES;      // [2] own CTA: slab sum complete (multicast commit)
   uint64_t* acce_bar = bars + 3 * T2_STAGES + 2;  // [2] leader: buffer drained by the epilogues of both CTAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * T2_STAGES + 4);
+  float* stage_s = reinterpret_cast<float*>(bars + 32);       // [T2_EPI_WARPS][32][33] transpose tiles of the store
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -194,7 +214,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
       // ================= TMA producer (each CTA loads its own 128 rows of A and 128 columns of B) ==========
       if (lane == 0) {
@@ -285,32 +305,31 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int s = g % T2_STAGES;
           const uint32_t ph = (g / T2_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
-          float4* ah = reinterpret_cast<float4*>(sA_hi + s * TC_TILE_BYTES);
-          float4* al = reinterpret_cast<float4*>(sA_lo + s * TC_TILE_BYTES);
-          float4* bh = reinterpret_cast<float4*>(sB_hi + s * TC_TILE_BYTES);
-          float4* bl = reinterpret_cast<float4*>(sB_lo + s * TC_TILE_BYTES);
+          const uint32_t ah = smem_u32(sA_hi + s * TC_TILE_BYTES) + 16u * tI, al = smem_u32(sA_lo + s * TC_TILE_BYTES) + 16u * tI;
+          const uint32_t bh = smem_u32(sB_hi + s * TC_TILE_BYTES) + 16u * tI, bl = smem_u32(sB_lo + s * TC_TILE_BYTES) + 16u * tI;
 #pragma unroll 4
-          for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
-            const int idx = e * 128 + tI;
-            float4 va = ah[idx], vb = bh[idx], h, l;
+          for (int e = 0; e < ((dbg & 2) ? 0 : TC_TILE_BYTES / 16 / 128); ++e) {
+            const uint32_t off = (uint32_t)e * 2048u;
+            const float4 va = lds128(ah + off), vb = lds128(bh + off);
+            float4 l;
             if (T2_RAW_HI) {
-              h.x = __uint_as_float(__float_as_uint(va.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(va.y) & 0xFFFFE000u);
-              h.z = __uint_as_float(__float_as_uint(va.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(va.w) & 0xFFFFE000u);
+              l.x = tf32_lo_of(va.x); l.y = tf32_lo_of(va.y); l.z = tf32_lo_of(va.z); l.w = tf32_lo_of(va.w);
             } else {
+              float4 h;
               h.x = to_tf32_rna(va.x); h.y = to_tf32_rna(va.y); h.z = to_tf32_rna(va.z); h.w = to_tf32_rna(va.w);
-              ah[idx] = h;
+              sts128(ah + off, h);
+              l.x = va.x - h.x; l.y = va.y - h.y; l.z = va.z - h.z; l.w = va.w - h.w;
             }
-            l.x = va.x - h.x; l.y = va.y - h.y; l.z = va.z - h.z; l.w = va.w - h.w;
-            al[idx] = l;
+            sts128(al + off, l);
             if (T2_RAW_HI) {
-              h.x = __uint_as_float(__float_as_uint(vb.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(vb.y) & 0xFFFFE000u);
-              h.z = __uint_as_float(__float_as_uint(vb.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(vb.w) & 0xFFFFE000u);
+              l.x = tf32_lo_of(vb.x); l.y = tf32_lo_of(vb.y); l.z = tf32_lo_of(vb.z); l.w = tf32_lo_of(vb.w);
             } else {
+              float4 h;
               h.x = to_tf32_rna(vb.x); h.y = to_tf32_rna(vb.y); h.z = to_tf32_rna(vb.z); h.w = to_tf32_rna(vb.w);
-              bh[idx] = h;
+              sts128(bh + off, h);
+              l.x = vb.x - h.x; l.y = vb.y - h.y; l.z = vb.z - h.z; l.w = vb.w - h.w;
             }
-            l.x = vb.x - h.x; l.y = vb.y - h.y; l.z = vb.z - h.z; l.w = vb.w - h.w;
-            bl[idx] = l;
+            sts128(bl + off, l);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
           __syncwarp();
@@ -319,7 +338,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ================= epilogue (warps 8..15: TMEM lane quadrant = warp % 4, column half = (warp - 8) / 4) ====
     const int quad = warp & 3;
     const int half = (warp - 8) >> 2;
@@ -337,6 +356,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          if (dbg & 4) break;
           uint32_t r[32];
           tmem_ld32(t_row + (uint32_t)(buf * T2_BN + c * 32), r);
 #pragma unroll
@@ -346,57 +366,115 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(acce_remote + 8u * buf);
       }
-      // ---- tile epilogue: this thread owns row m, columns n0 + half*128 .. +128 ----
-      const int64_t m = tl.m0 + (int64_t)rank * TC_ROWS + quad * 32 + lane;
-      if (m < p.M) {
-        float* Crow = p.C + tl.i0 * p.c_bs[0] + tl.i1 * p.c_bs[1] + tl.i2 * p.c_bs[2] + m * p.c_rs;
-        float gamma2 = 1.f, rown = 0.f;
-        const float* e_col = nullptr;
-        if (p.epi != VARGP_EPI_NONE) {
-          gamma2 = expf(2.f * p.e_theta[tl.i0 * p.e_theta_bs[0] + tl.i1 * p.e_theta_bs[1] + tl.i2 * p.e_theta_bs[2] + p.e_D]);
-          const float* e_row = p.e_row + tl.i0 * p.e_row_bs[0] + tl.i1 * p.e_row_bs[1] + tl.i2 * p.e_row_bs[2];
-          e_col = p.e_col + tl.i0 * p.e_col_bs[0] + tl.i1 * p.e_col_bs[1] + tl.i2 * p.e_col_bs[2];
-          rown = 0.5f * e_row[m];
-        }
-        const int64_t nbase = tl.n0 + half * 128;
+      // ---- tile epilogue.  After the drain a thread owns ROW m (TMEM lane) and 128 consecutive columns.  Stored
+      //      like that, every store instruction of a warp touches 32 different rows (measured: the store phase
+      //      took 44 % of the kernel).  For row-major C each 32 x 32 sub-block is therefore transposed through a
+      //      padded per-warp smem tile, so that a lane owns a COLUMN and a warp writes one full 128 B line per
+      //      instruction.  Column-major C (c_rs == 1) is already coalesced along the lanes and stored directly. ----
+      if (dbg & 1) continue;
+      const int64_t mrow0 = tl.m0 + (int64_t)rank * TC_ROWS + quad * 32;       // first row of this warp
+      const int64_t m = mrow0 + lane;
+      const int64_t nbase = tl.n0 + half * 128;
+      float* Cb = p.C + tl.i0 * p.c_bs[0] + tl.i1 * p.c_bs[1] + tl.i2 * p.c_bs[2];
+      float gamma2 = 1.f, rown = 0.f;
+      const float* e_col = nullptr;
+      if (p.epi != VARGP_EPI_NONE) {
+        gamma2 = expf(2.f * p.e_theta[tl.i0 * p.e_theta_bs[0] + tl.i1 * p.e_theta_bs[1] + tl.i2 * p.e_theta_bs[2] + p.e_D]);
+        const float* e_row = p.e_row + tl.i0 * p.e_row_bs[0] + tl.i1 * p.e_row_bs[1] + tl.i2 * p.e_row_bs[2];
+        e_col = p.e_col + tl.i0 * p.e_col_bs[0] + tl.i1 * p.e_col_bs[1] + tl.i2 * p.e_col_bs[2];
+        if (m < p.M) rown = 0.5f * e_row[m];
+      }
+      {
+        // explicit shared-space accesses (a generic LD/ST here costs address translation on every element) and
+        // rolled loops behind the staging tile: this code runs once per tile, so straight-line unrolled code only
+        // misses the instruction cache (measured: stall_no_inst was the top stall of the store phase)
+        const uint32_t tile = smem_u32(stage_s + (warp - 8) * (32 * 33));
+        const int Mi = (int)p.M, Ni = (int)p.N, mrow = (int)mrow0;
+        const bool sym = p.epi == VARGP_EPI_RBF_SYM, rbf = p.epi != VARGP_EPI_NONE;
+        const bool row_major = p.c_cs == 1;
 #pragma unroll
-        for (int j4 = 0; j4 < 128; j4 += 4) {
-          const int64_t n = nbase + j4;
-          if (n >= p.N) break;
-          float v[4];
-          bool keep[4];
+        for (int c = 0; c < 4; ++c) {
+          __syncwarp();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int64_t nn = n + u;
-            keep[u] = !((p.tri_c == VARGP_TRI_LOWER && nn > m) || (p.tri_c == VARGP_TRI_UPPER && nn < m));
-            float x = acc[j4 + u];
-            if (p.epi != VARGP_EPI_NONE) {
-              x = (nn < p.N) ? gamma2 * expf(x - rown - 0.5f * e_col[nn]) : 0.f;
-              if (p.epi == VARGP_EPI_RBF_SYM && m == nn) x = gamma2;
-            }
-            v[u] = x * p.alpha;
-          }
-          if (c_vec4 && n + 3 < p.N) {
-            float4* cp = reinterpret_cast<float4*>(Crow + n);
-            float4 o;
-            if (p.beta != 0.f) {
-              o = *cp;
-              o.x = keep[0] ? fmaf(p.beta, o.x, v[0]) : o.x; o.y = keep[1] ? fmaf(p.beta, o.y, v[1]) : o.y;
-              o.z = keep[2] ? fmaf(p.beta, o.z, v[2]) : o.z; o.w = keep[3] ? fmaf(p.beta, o.w, v[3]) : o.w;
-            } else {
-              o.x = keep[0] ? v[0] : 0.f; o.y = keep[1] ? v[1] : 0.f; o.z = keep[2] ? v[2] : 0.f; o.w = keep[3] ? v[3] : 0.f;
-            }
-            *cp = o;
-          } else {
+          for (int j = 0; j < 32; ++j)      // the RBF row term is subtracted here, where a thread still owns one row
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile + 4u * (lane * 33 + j)), "f"(acc[c * 32 + j] - rown) : "memory");
+          __syncwarp();
+          const int nc0 = (int)nbase + c * 32;
+          if (nc0 >= Ni) break;                                                // warp-uniform
+          if (row_major) {
+            const int n = nc0 + lane;                                          // this lane's column after the transpose
+            const bool n_ok = n < Ni;
+            float coln = 0.f;
+            if (rbf && n_ok) coln = 0.5f * e_col[n];
+            float* cp0 = Cb + (int64_t)mrow * p.c_rs + n;
+            // interior 32 x 32 blocks (no ragged edge, no triangle boundary, beta == 0) skip every per-element predicate
+            const bool kept = p.tri_c == VARGP_TRI_NONE || (p.tri_c == VARGP_TRI_LOWER && nc0 + 31 <= mrow) ||
+                              (p.tri_c == VARGP_TRI_UPPER && nc0 >= mrow + 31);
+            if (kept && !sym && p.beta == 0.f && mrow + 31 < Mi && nc0 + 31 < Ni) {
+              const float scale = gamma2 * p.alpha;
+#pragma unroll 1
+              for (int r0 = 0; r0 < 32; r0 += 8) {
+                float xv[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (n + u >= p.N) break;
-              float* cp = Crow + (n + u) * p.c_cs;
-              if (!keep[u]) {
-                if (p.beta == 0.f) *cp = 0.f;
-                continue;
+                for (int u = 0; u < 8; ++u)
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[u]) : "r"(tile + 4u * ((r0 + u) * 33 + lane)));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xv[u] = rbf ? scale * expf(xv[u] - coln) : xv[u] * p.alpha;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cp0[(int64_t)(r0 + u) * p.c_rs] = xv[u];
               }
-              *cp = (p.beta != 0.f) ? fmaf(p.beta, *cp, v[u]) : v[u];
+              continue;
+            }
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float xv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[u]) : "r"(tile + 4u * ((r0 + u) * 33 + lane)));
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (rbf) {
+                  xv[u] = gamma2 * expf(xv[u] - coln);
+                  if (sym && mrow + r0 + u == n) xv[u] = gamma2;
+                }
+                xv[u] *= p.alpha;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int mm = mrow + r0 + u;
+                float* cp = cp0 + (int64_t)(r0 + u) * p.c_rs;
+                const bool ok = n_ok && mm < Mi;
+                const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > mm) || (p.tri_c == VARGP_TRI_UPPER && n < mm);
+                if (p.beta != 0.f) {
+                  if (ok && !masked) *cp = fmaf(p.beta, *cp, xv[u]);
+                } else if (ok) {
+                  *cp = masked ? 0.f : xv[u];
+                }
+              }
+            }
+          } else {
+            // C not row-major (e.g. written through a transposed view): lanes run along m, which is then the
+            // coalesced direction already; the staging tile only serves as a dynamically indexable copy of acc[]
+            const int mm = (int)m;
+            float* cp0 = Cb + (int64_t)mm * p.c_rs;
+#pragma unroll 2
+            for (int j = 0; j < 32; ++j) {
+              const int n = nc0 + j;
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(tile + 4u * (lane * 33 + j)));
+              if (rbf) {
+                x = gamma2 * expf(x - ((n < Ni) ? 0.5f * e_col[n] : 0.f));
+                if (sym && mm == n) x = gamma2;
+              }
+              x *= p.alpha;
+              float* cp = cp0 + (int64_t)n * p.c_cs;
+              const bool ok = n < Ni && mm < Mi;
+              const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > mm) || (p.tri_c == VARGP_TRI_UPPER && n < mm);
+              if (p.beta != 0.f) {
+                if (ok && !masked) *cp = fmaf(p.beta, *cp, x);
+              } else if (ok) {
+                *cp = masked ? 0.f : x;
+              }
             }
           }
         }
@@ -419,6 +497,7 @@ static int g_t2_clusters = 74;      // CTA pairs that can be co-resident (SM cou
 static int64_t g_t2_min_tiles = 24;
 static int64_t g_t2_launches = 0;
 static bool g_t2_rna = false;
+static int g_t2_dbg = 0;           // VARGP_TC2_DBG: timing experiments only (results are wrong): 1 no store, 2 no split, 4 no drain
 
 int tc2_init() {
   cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
@@ -427,6 +506,8 @@ int tc2_init() {
   if (e != cudaSuccess) return (int)e;
   const char* rna = getenv("VARGP_TC2_RNA");
   if (rna) g_t2_rna = atoi(rna) != 0;
+  const char* dbg = getenv("VARGP_TC2_DBG");
+  if (dbg) g_t2_dbg = atoi(dbg);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   g_t2_clusters = sms / 2 > 0 ? sms / 2 : 1;
@@ -454,9 +535,9 @@ int tc2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p
   for (int i = 0; i < 3; ++i)
     if (p.nb[i] > 1 && p.c_bs[i] % 4 != 0) c_vec4 = 0;
   if (g_t2_rna)
-    gemm_tc2_kernel<false><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4);
+    gemm_tc2_kernel<false><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4, g_t2_dbg);
   else
-    gemm_tc2_kernel<true><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4);
+    gemm_tc2_kernel<true><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4, g_t2_dbg);
   ++g_t2_launches;
   return launch_status();
 }
