@@ -192,7 +192,8 @@ def run_gpu(args):
     cfg = dict(cfg, B=args.batch)
   B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
   global_B = B * world
-  use_graph = (not args.no_graph) and (world == 1 or args.graph_multi)
+  use_graph = (not args.no_graph) and (world == 1 or args.graph_multi) and wl != 'scaled'   # scaled: ~100 GB of
+  # workspaces live once in the eager allocator; a graph-private pool on top of the warm-up pool would not fit
   from vargp_b200.train import ElboStepper
   stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
                         use_graph=use_graph)

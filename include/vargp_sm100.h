@@ -100,6 +100,18 @@ int vargp_chol_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t 
 int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_ld, int64_t w_bs,
                 int64_t n, int64_t batch, void* stream);
 
+/* L = chol(A + jitter*I) and W = L^-1 in one call (both lower, strict upper zeroed).  Matrices of at least
+ * `min_n` rows (vargp_chol_config) are factored block-wise: nb x nb diagonal blocks by the vargp_chol / vargp_trtri
+ * kernels, the trailing updates, panel solves and the block merges of the inverse as batched 3xTF32 tensor-core
+ * GEMMs (potrf_blocked.cu); W and the strict upper triangle of L serve as scratch, so no workspace is needed.
+ * A, L, W must not alias.  Replaces var_gp/gp_utils.py:5-11 plus the solves of :89-92,124-134,175-182. */
+int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                   float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                   int32_t* info, void* stream);
+/* block size (multiple of 32; 0 keeps it) and minimum n (< 0 keeps it) of the blocked path;
+ * returns (min_n << 32) | block after the update. */
+int64_t vargp_chol_config(int64_t block, int64_t min_n);
+
 /* packed row-major lower triangle -> (C, M, M) with softplus on the diagonal, and its adjoint.
  * Replaces var_gp/gp_utils.py:22-49. */
 int vargp_tril_unpack(const float* vec, int64_t C, int64_t M, float* out, void* stream);
@@ -107,8 +119,9 @@ int vargp_tril_unpack_bwd(const float* Lbar, const float* vec, int64_t C, int64_
 
 /* kl += (1/H) sum_hc [ -sum_{i in last block} log W_ii - sum_i log Lu_ii + (|T_last|_F^2 + |nu_last|^2 - M)/2 ]
  * W (H,C,P,P), T (H,C,S,M,M), nu (H,C,P), Lu (C,M,M).  Replaces var_gp/vargp.py:182-190. */
+#define VARGP_KL_CHUNKS 16   /* partial sums per (h, c): work holds H*C*VARGP_KL_CHUNKS floats */
 int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu,
-                 int64_t H, int64_t C, int64_t P, int64_t M, float* kl, float* work /* H*C floats */, void* stream);
+                 int64_t H, int64_t C, int64_t P, int64_t M, float* kl, float* work, void* stream);
 int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g_kl,
                  int64_t H, int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream);
 int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar, void* stream);

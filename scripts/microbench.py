@@ -60,7 +60,7 @@ def main():
   ap.add_argument('--M', type=int, nargs='+', default=[64, 128, 256, 512, 1024, 2048, 4096])
   ap.add_argument('--B', type=int, default=65536)
   ap.add_argument('--iters', type=int, default=5)
-  ap.add_argument('--only', nargs='+', default=None, help='subset of: kxz kzz chol trtri trsm stream')
+  ap.add_argument('--only', nargs='+', default=None, help='subset of: kxz kzz chol trtri chol_inv trsm stream')
   ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'microbench.jsonl'))
   args = ap.parse_args()
   ops = vops.get_ops()
@@ -118,8 +118,12 @@ def main():
       emit('trtri', M, ms, mn, flops=H * C * P ** 3 / 3.0, nbytes=8.0 * H * C * P * P)
     else:
       ops.trtri(L, W)
+    if want('chol_inv'):
+      ms, mn = timeit(lambda: ops.chol_inv(Kzz, L, W, 1e-4, info), args.iters, small)
+      emit('chol_inv', M, ms, mn, flops=2.0 * H * C * P ** 3 / 3.0, nbytes=12.0 * H * C * P * P, info_max=int(info.max()),
+           block=ops.chol_config()[0], blocked=bool(P >= ops.chol_config()[1]))
     # accuracy spot check of the factorisation on one matrix (fp64 on device)
-    if want('chol') or want('trtri'):
+    if want('chol') or want('trtri') or want('chol_inv'):
       K0 = Kzz[0, 0].double() + 1e-4 * torch.eye(P, device=dev, dtype=torch.float64)
       L0, W0 = L[0, 0].double(), W[0, 0].double()
       e_l = ((L0 @ L0.T - K0).norm() / K0.norm()).item()

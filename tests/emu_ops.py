@@ -51,6 +51,10 @@ class EmuOps:
     eye = torch.eye(L.shape[-1], dtype=L.dtype, device=L.device).expand_as(L)
     W.copy_(torch.linalg.solve_triangular(L, eye, upper=False))
 
+  def chol_inv(self, K, L, W, jitter, info):
+    self.chol(K, L, jitter, info)
+    self.trtri(L, W)
+
   def kl_fwd(self, W, T, nu, Lu_t, M, kl):
     H = W.shape[0]
     P = W.shape[-1]

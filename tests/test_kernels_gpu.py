@@ -142,6 +142,61 @@ def test_chol_reports_non_pd(cuda_ops):
   assert info.tolist() == [0, 18, 0]
 
 
+@pytest.mark.parametrize('n,batch,nb', [(600, 4, 128), (1024, 3, 128), (450, 5, 64), (520, 2, 96), (2048, 2, 128),
+                                        (300, 6, 0), (129, 3, 128), (1000, 2, 256)])
+def test_chol_inv_blocked(cuda_ops, n, batch, nb):
+  """vargp_chol_inv: GEMM-driven blocked factorisation + inverse (potrf_blocked.cu) incl. ragged block counts;
+  nb = 0 is the small-matrix route through the one-CTA kernels."""
+  old = cuda_ops.chol_config()
+  try:
+    if nb:
+      cuda_ops.chol_config(nb, nb + 1)
+    else:
+      cuda_ops.chol_config(0, 1 << 20)
+    X = rnd(batch, n, n + 5, seed=n)
+    A = X @ X.transpose(-1, -2) / (n + 5) + 0.05 * torch.eye(n, dtype=torch.float64)
+    L64 = torch.linalg.cholesky(A + 1e-4 * torch.eye(n, dtype=torch.float64))
+    W64 = torch.linalg.solve_triangular(L64, torch.eye(n, dtype=torch.float64).expand(batch, n, n), upper=False)
+    # strided views (ld > n) with NaN-poisoned surroundings: nothing outside the n x n blocks may be read or written
+    Lbuf = torch.full((batch, n, n + 8), float('nan'), device='cuda')
+    Wbuf = torch.full((batch, n + 4, n + 4), float('nan'), device='cuda')
+    L, W = Lbuf[:, :, :n], Wbuf[:, :n, :n]
+    info = torch.full((batch,), -1, device='cuda', dtype=torch.int32)
+    Ad = dev(A)
+    A0 = Ad.clone()
+    cuda_ops.chol_inv(Ad, L, W, 1e-4, info)
+    assert int(info.abs().max()) == 0
+    assert torch.equal(Ad, A0)
+    close(L, L64, 2e-5, 'chol')
+    close(W, W64, 3e-5, 'inverse')
+    assert torch.equal(L.triu(1), torch.zeros_like(L)) and torch.equal(W.triu(1), torch.zeros_like(W))
+    assert torch.isnan(Lbuf[:, :, n:]).all() and torch.isnan(Wbuf[:, n:]).all() and torch.isnan(Wbuf[:, :, n:]).all()
+    # residuals in fp64: L L^T = A + jitter I and W L = I
+    Ld, Wd = L.double().cpu(), W.double().cpu()
+    Aj = A + 1e-4 * torch.eye(n, dtype=torch.float64)
+    assert ((Ld @ Ld.transpose(-1, -2) - Aj).norm() / Aj.norm()).item() < 2e-6
+    assert ((Wd @ Ld - torch.eye(n, dtype=torch.float64)).norm() / n ** 0.5).item() < 2e-4
+  finally:
+    cuda_ops.chol_config(*old)
+
+
+def test_chol_inv_blocked_reports_first_bad_pivot(cuda_ops):
+  old = cuda_ops.chol_config()
+  try:
+    cuda_ops.chol_config(64, 65)
+    n = 300
+    A = torch.eye(n, dtype=torch.float64).repeat(3, 1, 1)
+    A[1, 170, 170] = -1.0
+    A[1, 250, 250] = -1.0
+    A[2, 3, 3] = -2.0
+    L, W = torch.empty(3, n, n, device='cuda'), torch.empty(3, n, n, device='cuda')
+    info = torch.zeros(3, device='cuda', dtype=torch.int32)
+    cuda_ops.chol_inv(dev(A), L, W, 1e-4, info)
+    assert info.tolist() == [0, 171, 4]
+  finally:
+    cuda_ops.chol_config(*old)
+
+
 def test_chol_strided_block_view(cuda_ops):
   """chol / trtri on diagonal blocks of a bigger matrix (ld > n), as the blocked large-P schedule uses them."""
   n, P = 64, 256
@@ -174,7 +229,8 @@ def test_tril_unpack(cuda_ops, C, M):
   close(vb, vb64, 1e-6, 'tril_unpack_bwd')
 
 
-@pytest.mark.parametrize('H,C,S,M,B,D', [(3, 10, 3, 20, 200, 784), (2, 3, 1, 7, 33, 37), (1, 4, 2, 9, 21, 16)])
+@pytest.mark.parametrize('H,C,S,M,B,D', [(3, 10, 3, 20, 200, 784), (2, 3, 1, 7, 33, 37), (1, 4, 2, 9, 21, 16),
+                                         (2, 2, 1, 300, 40, 16)])
 def test_marginal_kl_kernels(cuda_ops, H, C, S, M, B, D):
   P = S * M
   W = (rnd(H, C, P, P, seed=1, scale=0.1).tril() + torch.eye(P, dtype=torch.float64))

@@ -410,16 +410,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // interior 32 x 32 blocks (no ragged edge, no triangle boundary, beta == 0) skip every per-element predicate
             const bool kept = p.tri_c == VARGP_TRI_NONE || (p.tri_c == VARGP_TRI_LOWER && nc0 + 31 <= mrow) ||
                               (p.tri_c == VARGP_TRI_UPPER && nc0 >= mrow + 31);
-            if (kept && !sym && p.beta == 0.f && mrow + 31 < Mi && nc0 + 31 < Ni) {
+            if (kept && !sym && mrow + 31 < Mi && nc0 + 31 < Ni) {
               const float scale = gamma2 * p.alpha;
+              const bool accum = p.beta != 0.f;                                // warp-uniform
 #pragma unroll 1
               for (int r0 = 0; r0 < 32; r0 += 8) {
-                float xv[8];
+                float xv[8], cv[8];
+                if (accum) {                       // 8 independent coalesced 128 B reads in flight per warp
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) cv[u] = cp0[(int64_t)(r0 + u) * p.c_rs];
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[u]) : "r"(tile + 4u * ((r0 + u) * 33 + lane)));
 #pragma unroll
                 for (int u = 0; u < 8; ++u) xv[u] = rbf ? scale * expf(xv[u] - coln) : xv[u] * p.alpha;
+                if (accum) {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) xv[u] = fmaf(p.beta, cv[u], xv[u]);
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) cp0[(int64_t)(r0 + u) * p.c_rs] = xv[u];
               }

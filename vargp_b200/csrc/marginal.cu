@@ -77,52 +77,65 @@ __global__ void sym_phi_kernel(float* __restrict__ X, int64_t n) {
 }
 
 // KL(u) forward, two deterministic stages (bit-reproducible: no float atomics):
-//   stage 1: one block per (h, c) -> part[g];  stage 2: one warp sums part[] in a fixed order.   (vargp.py:182-190)
+//   stage 1: grid (kKlChunks, H*C): chunk k of (h, c) sums its slice of |T_t|_F^2 (chunk 0 also the O(M) terms)
+//            -> part[g][k];  stage 2: one warp sums part[] in a fixed order.                       (vargp.py:182-190)
+constexpr int kKlChunks = VARGP_KL_CHUNKS;
+
 __global__ void __launch_bounds__(256)
 kl_fwd_part_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
                    const float* __restrict__ Lu, int64_t C, int64_t P, int64_t M, float* __restrict__ part) {
   __shared__ float scratch[32];
-  const int64_t g = blockIdx.x, c = g % C, S = P / M, Q = P - M;
+  const int64_t g = blockIdx.y, c = g % C, S = P / M, Q = P - M;
   const float* w = W + g * P * P;
   const float* t = T + (g * S + (S - 1)) * M * M;
   const float* nug = nu + g * P + Q;
   const float* lu = Lu + c * M * M;
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-    acc -= logf(w[(Q + i) * P + (Q + i)]);
-    acc -= logf(lu[i * M + i]);
-    const float v = nug[i];
-    acc += 0.5f * (v * v - 1.f);
+  if (blockIdx.x == 0) {
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+      acc -= logf(w[(Q + i) * P + (Q + i)]);
+      acc -= logf(lu[i * M + i]);
+      const float v = nug[i];
+      acc += 0.5f * (v * v - 1.f);
+    }
   }
-  for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) {
-    const float v = t[e];
-    acc = fmaf(0.5f * v, v, acc);
+  // rows of T_t are dealt round-robin to the chunks; only the lower triangle is non-zero
+  for (int64_t i = blockIdx.x; i < M; i += kKlChunks) {
+    const float* row = t + i * M;
+    for (int64_t j = threadIdx.x; j <= i; j += blockDim.x) {
+      const float v = row[j];
+      acc = fmaf(0.5f * v, v, acc);
+    }
   }
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) part[g] = acc;
+  if (threadIdx.x == 0) part[g * kKlChunks + blockIdx.x] = acc;
 }
 
 __global__ void __launch_bounds__(32)
-kl_fwd_sum_kernel(const float* __restrict__ part, int64_t G, int64_t H, float* __restrict__ kl) {
+kl_fwd_sum_kernel(const float* __restrict__ part, int64_t n, int64_t H, float* __restrict__ kl) {
   float acc = 0.f;
-  for (int64_t g = threadIdx.x; g < G; g += 32) acc += part[g];
+  for (int64_t g = threadIdx.x; g < n; g += 32) acc += part[g];
   acc = warp_sum(acc);
   if (threadIdx.x == 0) kl[0] += acc / (float)H;
 }
 
+// grid (row chunks, H*C)
 __global__ void __launch_bounds__(256)
 kl_bwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
               const float* __restrict__ g_kl, int64_t H, int64_t C, int64_t P, int64_t M,
               float* __restrict__ Wbar, float* __restrict__ Tbar, float* __restrict__ nubar) {
-  const int64_t g = blockIdx.x, S = P / M, Q = P - M;
+  const int64_t g = blockIdx.y, S = P / M, Q = P - M;
   const float s = g_kl[0] / (float)H;
   const float* t = T + (g * S + (S - 1)) * M * M;
   float* tb = Tbar + (g * S + (S - 1)) * M * M;
-  for (int64_t e = threadIdx.x; e < M * M; e += blockDim.x) tb[e] = fmaf(s, t[e], tb[e]);
-  for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-    nubar[g * P + Q + i] = fmaf(s, nu[g * P + Q + i], nubar[g * P + Q + i]);
-    const int64_t o = g * P * P + (Q + i) * P + (Q + i);
-    Wbar[o] -= s / W[o];
+  for (int64_t i = blockIdx.x; i < M; i += gridDim.x)
+    for (int64_t j = threadIdx.x; j <= i; j += blockDim.x) tb[i * M + j] = fmaf(s, t[i * M + j], tb[i * M + j]);
+  if (blockIdx.x == 0) {
+    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
+      nubar[g * P + Q + i] = fmaf(s, nu[g * P + Q + i], nubar[g * P + Q + i]);
+      const int64_t o = g * P * P + (Q + i) * P + (Q + i);
+      Wbar[o] -= s / W[o];
+    }
   }
 }
 
@@ -208,17 +221,21 @@ extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream) {
 extern "C" int vargp_kl_fwd(const float* W, const float* T, const float* nu, const float* Lu, int64_t H, int64_t C,
                             int64_t P, int64_t M, float* kl, float* work, void* stream) {
   if (!W || !T || !nu || !Lu || !kl || !work || M < 1 || P % M) return VARGP_ERR_ARG;
-  kl_fwd_part_kernel<<<(unsigned)(H * C), 256, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, C, P, M, work);
+  if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
+  kl_fwd_part_kernel<<<dim3(kKlChunks, (unsigned)(H * C)), 256, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, C, P, M, work);
   int rc = launch_status();
   if (rc) return rc;
-  kl_fwd_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(work, H * C, H, kl);
+  kl_fwd_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(work, H * C * kKlChunks, H, kl);
   return launch_status();
 }
 
 extern "C" int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g_kl, int64_t H,
                             int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream) {
   if (!W || !T || !nu || !g_kl || !Wbar || !Tbar || !nubar || M < 1 || P % M) return VARGP_ERR_ARG;
-  kl_bwd_kernel<<<(unsigned)(H * C), 256, 0, (cudaStream_t)stream>>>(W, T, nu, g_kl, H, C, P, M, Wbar, Tbar, nubar);
+  if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
+  const unsigned chunks = (unsigned)(M < 64 ? 1 : (M / 32 > 128 ? 128 : M / 32));
+  kl_bwd_kernel<<<dim3(chunks, (unsigned)(H * C)), 256, 0, (cudaStream_t)stream>>>(W, T, nu, g_kl, H, C, P, M, Wbar,
+                                                                                   Tbar, nubar);
   return launch_status();
 }
 

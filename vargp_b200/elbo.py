@@ -79,8 +79,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   # (3) W = chol(Kzz + eps I)^-1                                               [gp_utils.py:5-11]
   L, W = new(H, C, P, P), new(H, C, P, P)
   info = torch.zeros(H * C, device=dev, dtype=torch.int32)
-  ops.chol(Kzz, L, JITTER, info)
-  ops.trtri(L, W)
+  ops.chol_inv(Kzz, L, W, JITTER, info)
 
   # (4) whitened variational parameters (block diagonal)
   T, nu = new(H, C, S, M, M), new(H, C, P)
@@ -153,7 +152,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
     ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower', tag='Wbar+=V*Abart')
     # Tbar_s = V_s TVg_s^T ; nubar = V gm
-    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar, tag='Tbar=Vs*TVgt')
+    # (only the lower triangle of Tbar is ever consumed: T = W_ss Lu_s is lower triangular)
+    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar, c_tri='lower', tag='Tbar=Vs*TVgt')
     ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
   if g_kl is not None:
     # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block
@@ -161,10 +161,12 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
 
   # whitening adjoint: Wbar_ss += tril(Tbar_s Lu_s^T + nubar_s m_s^T); Lu_bar_s = sum_h W_ss^T Tbar_s ; m_bar_s = sum_h W_ss^T nubar_s
   Wbd = _blocks(Wbar, S, M)
-  ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
+  ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., a_tri='lower', b_tri='upper', c_tri='lower', tag='whiten_adj',
+           zeroed=True)
   ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
   Lubar_h = new(H, C, S, M, M)
-  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', c_tri='lower', tag='whiten_adj', zeroed=True)
+  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', b_tri='lower', c_tri='lower', tag='whiten_adj',
+           zeroed=True)
   mbar_h = new(H, C, S, M, 1)
   ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper', tag='whiten_adj', zeroed=True)
   Lu_bar = Lubar_h.sum(0).permute(1, 0, 2, 3).contiguous()      # (S, C, M, M)

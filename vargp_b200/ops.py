@@ -15,6 +15,7 @@ _LIB_PATH = os.path.join(_HERE, 'libvargp_sm100.so')
 
 _TRI = {None: 0, 'lower': 1, 'upper': 2}
 EPI_NONE, EPI_RBF, EPI_RBF_SYM = 0, 1, 2
+KL_CHUNKS = 16    # VARGP_KL_CHUNKS (include/vargp_sm100.h)
 
 i64 = ctypes.c_int64
 f32p = ctypes.c_void_p
@@ -62,6 +63,9 @@ def _load():
   lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
+  lib.vargp_chol_inv.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
+  lib.vargp_chol_config.argtypes = [i64, i64]
+  lib.vargp_chol_config.restype = i64
   lib.vargp_tril_unpack.argtypes = [vp, i64, i64, vp, vp]
   lib.vargp_tril_unpack_bwd.argtypes = [vp, vp, i64, i64, vp, vp]
   lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
@@ -122,7 +126,7 @@ class CudaOps:
     self.tc_calls = self.simt_calls = 0
 
   # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
-  _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'tril_unpack',
+  _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'chol_inv', 'tril_unpack',
                  'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'marginal_reduce', 'marginal_bwd_prep',
                  'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step')
 
@@ -136,9 +140,9 @@ class CudaOps:
         # algorithmic bytes of a streaming kernel: every tensor argument is touched once
         nbytes = sum(t.numel() * t.element_size() for t in a if isinstance(t, torch.Tensor))
         flops = 0.0
-        if _name in ('chol', 'trtri'):
+        if _name in ('chol', 'trtri', 'chol_inv'):
           n = a[0].shape[-1]
-          flops = (a[0].numel() // (n * n)) * n ** 3 / 3.0
+          flops = (a[0].numel() // (n * n)) * n ** 3 / 3.0 * (2 if _name == 'chol_inv' else 1)
         return self._timed(_name, _name, flops, nbytes, lambda: _fn(self, *a, **kw))
       setattr(self, name, timed)
 
@@ -344,6 +348,21 @@ class CudaOps:
       raise VargpError('trtri: shape mismatch')
     self._check(self.lib.vargp_trtri(lp, lld, lbs, wp, wld, wbs, n, batch, self._stream(W)), 'trtri')
 
+  def chol_inv(self, K, L, W, jitter, info):
+    """L = chol(K + jitter I), W = L^-1 (blocked, tensor-core driven for large n; see potrf_blocked.cu)."""
+    ap, ald, abs_, n, batch = self._mat_batch(K, 'K')
+    lp, lld, lbs, n2, batch2 = self._mat_batch(L, 'L')
+    wp, wld, wbs, n3, batch3 = self._mat_batch(W, 'W')
+    if not ((n, batch) == (n2, batch2) == (n3, batch3)) or info.numel() != batch or info.dtype != torch.int32:
+      raise VargpError('chol_inv: shape mismatch')
+    self._check(self.lib.vargp_chol_inv(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
+                                        info.data_ptr(), self._stream(L)), 'chol_inv')
+
+  def chol_config(self, block=0, min_n=-1):
+    """Set block size / minimum n of the blocked factorisation; returns (block, min_n) in effect."""
+    r = int(self.lib.vargp_chol_config(int(block), int(min_n)))
+    return r & 0xffffffff, r >> 32
+
   def tril_unpack(self, vec, out):
     C, M = out.shape[0], out.shape[-1]
     if tuple(vec.shape) != (C, M * (M + 1) // 2):
@@ -359,7 +378,7 @@ class CudaOps:
   # -- KL(u) ----------------------------------------------------------------------------------
   def kl_fwd(self, W, T, nu, Lu_t, M, kl):
     H, C, P, _ = W.shape
-    work = torch.empty(H * C, device=W.device, dtype=W.dtype)
+    work = torch.empty(H * C * KL_CHUNKS, device=W.device, dtype=W.dtype)
     self._check(self.lib.vargp_kl_fwd(_f32(W, 'W'), _f32(T, 'T'), _f32(nu, 'nu'), _f32(Lu_t, 'Lu_t'), H, C, P, M,
                                       _f32(kl, 'kl'), work.data_ptr(), self._stream(W)), 'kl_fwd')
 
