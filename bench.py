@@ -176,13 +176,20 @@ def cpu_reference_steps(wl, task, steps, warmup, budget_s, threads=None):
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
   import torch.distributed as dist
+  import datetime
   rank = int(os.environ.get('RANK', 0))
+  t_start = time.time()
+
+  def log(msg):
+    if args.verbose:
+      print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}', file=sys.stderr, flush=True)
   world = int(os.environ.get('WORLD_SIZE', 1))
   local = int(os.environ.get('LOCAL_RANK', 0))
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   if world > 1:
-    dist.init_process_group('nccl', device_id=dev)
+    dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=120))
+    log('process group up')
   from vargp_b200 import ops as vops
   wl, task = args.workload, args.task
   cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
@@ -244,6 +251,7 @@ def run_gpu(args):
     launches = stepper.launches_per_step * K          # replayed from the captured CUDA graph
   clocks = sampler.stop() if rank == 0 else None
   gp.check_errors()
+  log(f'timed region done: {ms / K:.3f} ms/step')
 
   # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the three loss terms ----
   xh, yh = synth_batches(8, B, D, C, task, dev, seed=100 + rank, pin=True)
@@ -256,21 +264,22 @@ def run_gpu(args):
   for i in range(3):
     e2e_step(i)
   ms_e2e = timed(e2e_step, K)
+  log(f'e2e done: {ms_e2e / K:.3f} ms/step')
 
   # ---- per-kernel device times (separate instrumented pass, never inside a timed region) ----
-  prof = None
-  if rank == 0:
-    stepper.use_graph = False                         # eager launches so that each one can be bracketed by events
-    ops.profile_start()
-    nprof = 3
-    for i in range(nprof):
-      step(xs[i % n_pool], ys[i % n_pool])
-    prof = ops.profile_stop()
-    stepper.use_graph = use_graph
-    for d in prof.values():
-      for k in ('ms', 'flops', 'bytes'):
-        d[k] /= nprof
-      d['calls'] //= nprof
+  # (every rank runs it: the step contains the gradient all-reduce; only rank 0's record is reported)
+  stepper.use_graph = False                           # eager launches so that each one can be bracketed by events
+  ops.profile_start()
+  nprof = 3
+  for i in range(nprof):
+    step(xs[i % n_pool], ys[i % n_pool])
+  prof = ops.profile_stop()
+  stepper.use_graph = use_graph
+  for d in prof.values():
+    for k in ('ms', 'flops', 'bytes'):
+      d[k] /= nprof
+    d['calls'] //= nprof
+  log('instrumented pass done')
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -372,6 +381,7 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
   ap.add_argument('--graph-multi', action='store_true', help='also capture the step (incl. the NCCL all-reduce) when N > 1')
+  ap.add_argument('--verbose', action='store_true', help='progress lines on stderr')
   ap.add_argument('--detail', action='store_true', help='add per-call-site kernel times to the JSON line')
   args = ap.parse_args()
   if args.task is None:
