@@ -126,21 +126,25 @@ int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g
                  int64_t H, int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream);
 int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar, void* stream);
 
-/* f_mean[g][b] = sum_p nu[g][p] V[g][p][b];
- * f_var[g][b] = gamma2 - sum V^2 + sum TV^2 + jitter * sum A^2.   (var_gp/gp_utils.py:178-186) */
-int vargp_marginal_reduce(const float* V, const float* TV, const float* A, const float* nu,
+/* Predictive marginal (var_gp/gp_utils.py:178-186) from V = W Kzx and NV = N V, where
+ * N = blockdiag(T_s T_s^T) + jitter W W^T (P x P, symmetric) collects everything quadratic in V:
+ *   f_mean[g][b] = sum_p nu[g][p] V[g][p][b];
+ *   f_var[g][b]  = gamma2 + sum_p V (NV - V)   ( = gamma2 - |V_b|^2 + sum_s |T_s^T V_sb|^2 + jitter |W^T V_b|^2 ). */
+int vargp_marginal_reduce(const float* V, const float* NV, const float* nu,
                           const float* theta, int64_t theta_rs, int64_t D,
-                          int64_t H, int64_t C, int64_t P, int64_t B, float jitter,
+                          int64_t H, int64_t C, int64_t P, int64_t B,
                           float* f_mean, float* f_var, void* stream);
-/* Vbar = nu gm^T - 2 V gv;  A *= 2 jitter gv;  TV *= 2 gv;  theta_bar[h][D] += 2 gamma2 sum_cb gv */
-int vargp_marginal_bwd_prep(const float* V, float* TV, float* A, const float* nu,
+/* adjoint prologue: Vbar = nu gm^T + 2 gv (NV - V) (Vbar may alias NV);  Vg = gv V (so that Nbar = Vg V^T);
+ * theta_bar[h][D] += 2 gamma2 sum_cb gv */
+int vargp_marginal_bwd_prep(const float* V, const float* NV, const float* nu,
                             const float* g_mean, const float* g_var,
                             const float* theta, int64_t theta_rs, int64_t D,
-                            int64_t H, int64_t C, int64_t P, int64_t B, float jitter,
-                            float* Vbar, float* theta_bar, void* stream);
+                            int64_t H, int64_t C, int64_t P, int64_t B,
+                            float* Vbar, float* Vg, float* theta_bar, void* stream);
 
-/* X <- (Phi(X) + Phi(X)^T)/2 in place, batch of n x n (only the lower triangle of X is read) */
-int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream);
+/* batch of n x n, in place, only the lower triangle of X is read.
+ * mirror == 0: X <- (Phi(X) + Phi(X)^T)/2 (Cholesky adjoint);  mirror != 0: X_ji <- X_ij (symmetric completion) */
+int vargp_sym_phi(float* X, int64_t n, int64_t batch, int mirror, void* stream);
 
 /* Kbar *= K (elementwise, in place); rsum[g][i] = row sums; csum[h][j] += sum over (c,i) (optional).
  * Kbar, K are (H, C, Pa, Pb).  With dsum (symmetric Gram, Pa == Pb) the diagonal products are moved to

@@ -147,8 +147,16 @@ def main():
           f_mean, f_var = torch.empty(H, C, args.B, device=dev), torch.empty(H, C, args.B, device=dev)
           A = torch.empty_like(V)
           ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper', zeroed=True)
-          ms, mn = timeit(lambda: ops.marginal_reduce(V, Kzx, A, nu, theta, 1e-4, f_mean, f_var), args.iters, False)
-          emit('marginal_reduce', M, ms, mn, nbytes=4.0 * (3 * H * C * P * args.B + 2 * H * C * args.B))
+          ms, mn = timeit(lambda: ops.marginal_reduce(V, A, nu, theta, f_mean, f_var), args.iters, False)
+          emit('marginal_reduce', M, ms, mn, nbytes=4.0 * (2 * H * C * P * args.B + 2 * H * C * args.B))
+          g_mean, g_var, th_bar = torch.randn_like(f_mean), torch.randn_like(f_var), torch.zeros_like(theta)
+          Vg = torch.empty_like(V)
+          ms, mn = timeit(lambda: ops.marginal_bwd_prep(V, A, nu, g_mean, g_var, theta, A, Vg, th_bar), args.iters, False)
+          emit('marginal_bwd_prep', M, ms, mn, nbytes=4.0 * (4 * H * C * P * args.B + 2 * H * C * args.B))
+          rs, cs = torch.empty(H, C, P, device=dev), torch.zeros(H, args.B, device=dev)
+          ms, mn = timeit(lambda: ops.rbf_bwd_prep(Vg, Kzx, rs, cs), args.iters, False)
+          emit('rbf_bwd_prep', M, ms, mn, nbytes=4.0 * 3 * H * C * P * args.B)
+          del Vg
           del A
         del V
       del Kzx

@@ -75,22 +75,22 @@ class EmuOps:
   def kl_bwd_lu(self, Lu_t, g_kl, Lu_bar_t):
     Lu_bar_t.diagonal(dim1=-2, dim2=-1).sub_(g_kl / Lu_t.diagonal(dim1=-2, dim2=-1))
 
-  def marginal_reduce(self, V, TV, A, nu, theta, jitter, f_mean, f_var):
+  def marginal_reduce(self, V, NV, nu, theta, f_mean, f_var):
     g2 = torch.exp(2. * theta[:, -1]).view(-1, 1, 1)
     f_mean.copy_((V * nu.unsqueeze(-1)).sum(-2))
-    f_var.copy_(g2 - (V * V).sum(-2) + (TV * TV).sum(-2) + jitter * (A * A).sum(-2))
+    f_var.copy_(g2 + (V * (NV - V)).sum(-2))
 
-  def marginal_bwd_prep(self, V, TV, A, nu, g_mean, g_var, theta, jitter, Vbar, theta_bar):
+  def marginal_bwd_prep(self, V, NV, nu, g_mean, g_var, theta, Vbar, Vg, theta_bar):
+    """Vbar may alias NV."""
     gv = g_var.unsqueeze(-2)
     theta_bar[:, -1] += 2. * torch.exp(2. * theta[:, -1]) * g_var.sum((1, 2))
-    Vbar.copy_(nu.unsqueeze(-1) * g_mean.unsqueeze(-2) - 2. * V * gv)
-    A.mul_(2. * jitter * gv)
-    TV.mul_(2. * gv)
+    Vbar.copy_(nu.unsqueeze(-1) * g_mean.unsqueeze(-2) + 2. * gv * (NV - V))
+    Vg.copy_(V * gv)
 
-  def sym_phi(self, X):
+  def sym_phi(self, X, mirror=False):
     low = torch.tril(X, -1)
     d = torch.diag_embed(X.diagonal(dim1=-2, dim2=-1))
-    X.copy_(0.5 * (low + low.transpose(-1, -2) + d))
+    X.copy_((1.0 if mirror else 0.5) * (low + low.transpose(-1, -2) + d))
 
   def rbf_bwd_prep(self, Kbar, K, rsum, csum, dsum=None):
     Kbar.mul_(K)

@@ -237,16 +237,16 @@ def test_marginal_kl_kernels(cuda_ops, H, C, S, M, B, D):
   T, nu = rnd(H, C, S, M, M, seed=2).tril(), rnd(H, C, P, seed=3)
   Lu = rnd(C, M, M, seed=4, scale=0.1).tril() + torch.eye(M, dtype=torch.float64)
   theta = rnd(H, D + 1, seed=5, scale=0.1)
-  V, TV, A = rnd(H, C, P, B, seed=6), rnd(H, C, P, B, seed=7), rnd(H, C, P, B, seed=8)
+  V, NV = rnd(H, C, P, B, seed=6), rnd(H, C, P, B, seed=7)
   kl64 = torch.zeros((), dtype=torch.float64)
   EMU.kl_fwd(W, T, nu, Lu, M, kl64)
   kl = torch.zeros((), device='cuda')
   cuda_ops.kl_fwd(dev(W), dev(T), dev(nu), dev(Lu), M, kl)
   close(kl, kl64, 1e-5, 'kl_fwd')
   fm64, fv64 = torch.empty(H, C, B, dtype=torch.float64), torch.empty(H, C, B, dtype=torch.float64)
-  EMU.marginal_reduce(V, TV, A, nu, theta, 1e-4, fm64, fv64)
+  EMU.marginal_reduce(V, NV, nu, theta, fm64, fv64)
   fm, fv = torch.empty(H, C, B, device='cuda'), torch.empty(H, C, B, device='cuda')
-  cuda_ops.marginal_reduce(dev(V), dev(TV), dev(A), dev(nu), dev(theta), 1e-4, fm, fv)
+  cuda_ops.marginal_reduce(dev(V), dev(NV), dev(nu), dev(theta), fm, fv)
   close(fm, fm64, 1e-5, 'f_mean'); close(fv, fv64, 1e-5, 'f_var')
   # adjoint helpers
   g_kl = torch.tensor([0.7], dtype=torch.float64)
@@ -261,18 +261,20 @@ def test_marginal_kl_kernels(cuda_ops, H, C, S, M, B, D):
   cuda_ops.kl_bwd_lu(dev(Lu), dev(g_kl), Lb)
   close(Lb, Lb64, 1e-6, 'kl_bwd_lu')
   gm, gv = rnd(H, C, B, seed=13), rnd(H, C, B, seed=14)
-  Vb64, thb64 = torch.empty(H, C, P, B, dtype=torch.float64), rnd(H, D + 1, seed=15)
+  Vb64, Vg64, thb64 = torch.empty(H, C, P, B, dtype=torch.float64), torch.empty(H, C, P, B, dtype=torch.float64), rnd(H, D + 1, seed=15)
   thb = dev(thb64)
-  TV2, A2 = TV.clone(), A.clone()
-  EMU.marginal_bwd_prep(V, TV2, A2, nu, gm, gv, theta, 1e-4, Vb64, thb64)
-  TVd, Ad, Vb = dev(TV), dev(A), torch.empty(H, C, P, B, device='cuda')
-  cuda_ops.marginal_bwd_prep(dev(V), TVd, Ad, dev(nu), dev(gm), dev(gv), dev(theta), 1e-4, Vb, thb)
-  close(Vb, Vb64, 1e-6, 'Vbar'); close(TVd, TV2, 1e-6, 'TVg'); close(Ad, A2, 1e-6, 'Abar'); close(thb, thb64, 1e-5, 'thbar')
+  EMU.marginal_bwd_prep(V, NV, nu, gm, gv, theta, Vb64, Vg64, thb64)
+  NVd, Vg = dev(NV), torch.empty(H, C, P, B, device='cuda')
+  cuda_ops.marginal_bwd_prep(dev(V), NVd, dev(nu), dev(gm), dev(gv), dev(theta), NVd, Vg, thb)     # Vbar aliases NV
+  close(NVd, Vb64, 1e-6, 'Vbar'); close(Vg, Vg64, 1e-6, 'Vg'); close(thb, thb64, 1e-5, 'thbar')
   X64 = rnd(H, C, P, P, seed=16)
   Xd = dev(X64)
   EMU.sym_phi(X64)
   cuda_ops.sym_phi(Xd)
   close(Xd, X64, 1e-6, 'sym_phi')
+  EMU.sym_phi(X64, mirror=True)
+  cuda_ops.sym_phi(Xd, mirror=True)
+  close(Xd, X64, 1e-6, 'sym_mirror')
 
 
 @pytest.mark.parametrize('H,C,P,B,D', [(3, 10, 60, 200, 784), (2, 3, 21, 33, 37), (1, 4, 18, 21, 2)])

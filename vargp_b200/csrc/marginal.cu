@@ -4,60 +4,116 @@
 
 namespace vargp {
 
-// f_mean[g][b] = sum_p nu[g][p] V[g][p][b]; f_var = gamma2 - sum V^2 + sum TV^2 + jitter sum A^2
-// grid (B tiles, G); algorithmic bytes 4*(3*G*P*B + 2*G*B).          (gp_utils.py:178-186)
+// f_mean[g][b] = sum_p nu[g][p] V[g][p][b];  f_var[g][b] = gamma2 + sum_p V (NV - V)
+// (NV = N V with N = blockdiag(T_s T_s^T) + jitter W W^T: gamma2 - |V|^2 + |T^T V|^2 + jitter |W^T V|^2)
+// grid (B tiles, G); thread = one minibatch column, 4 independent accumulator chains over p.
+// Algorithmic bytes 4*(2*G*P*B + 2*G*B).                                           (gp_utils.py:178-186)
 __global__ void __launch_bounds__(128)
-marginal_reduce_kernel(const float* __restrict__ V, const float* __restrict__ TV, const float* __restrict__ A,
-                       const float* __restrict__ nu, const float* __restrict__ theta, int64_t theta_rs, int64_t D,
-                       int64_t C, int64_t P, int64_t B, float jitter,
-                       float* __restrict__ f_mean, float* __restrict__ f_var) {
+marginal_reduce_kernel(const float* __restrict__ V, const float* __restrict__ NV, const float* __restrict__ nu,
+                       const float* __restrict__ theta, int64_t theta_rs, int64_t D, int64_t C, int64_t P,
+                       int64_t B, float* __restrict__ f_mean, float* __restrict__ f_var) {
   const int64_t g = blockIdx.y;
   const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (b >= B) return;
   const float* v = V + g * P * B + b;
-  const float* tv = TV + g * P * B + b;
-  const float* a = A + g * P * B + b;
+  const float* nv = NV + g * P * B + b;
   const float* nug = nu + g * P;
-  float m = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-  for (int64_t p = 0; p < P; ++p) {
-    const float vv = v[p * B], tt = tv[p * B], aa = a[p * B];
-    m = fmaf(__ldg(nug + p), vv, m);
-    q1 = fmaf(vv, vv, q1);
-    q2 = fmaf(tt, tt, q2);
-    q3 = fmaf(aa, aa, q3);
+  float m[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t p = 0;
+  for (; p + 4 <= P; p += 4) {
+    float vv[4], nn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vv[u] = v[(p + u) * B];
+      nn[u] = nv[(p + u) * B];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      m[u] = fmaf(__ldg(nug + p + u), vv[u], m[u]);
+      q[u] = fmaf(vv[u], nn[u] - vv[u], q[u]);
+    }
+  }
+  for (; p < P; ++p) {
+    const float vv = v[p * B], nn = nv[p * B];
+    m[0] = fmaf(__ldg(nug + p), vv, m[0]);
+    q[0] = fmaf(vv, nn - vv, q[0]);
   }
   const float gamma2 = expf(2.f * theta[(g / C) * theta_rs + D]);
-  f_mean[g * B + b] = m;
-  f_var[g * B + b] = gamma2 - q1 + q2 + jitter * q3;
+  f_mean[g * B + b] = (m[0] + m[1]) + (m[2] + m[3]);
+  f_var[g * B + b] = gamma2 + ((q[0] + q[1]) + (q[2] + q[3]));
 }
 
-// Vbar = nu gm^T - 2 V gv; A *= 2 jitter gv; TV *= 2 gv; theta_bar[h][D] += 2 gamma2 sum_{c,b} gv
-// grid (B tiles, P chunks, G)
-constexpr int kPrepPch = 16;
+// Vbar = nu gm^T + 2 gv (NV - V)  (Vbar may alias NV);  Vg = gv V;  theta_bar[h][D] += 2 gamma2 sum_{c,b} gv
+// grid (B tiles of 128*VEC, P chunks of kPrepPch rows, G); VEC = 4: float4 along the minibatch axis.
+// Algorithmic bytes 4*(4*G*P*B + 2*G*B).
+constexpr int kPrepPch = 8;
+template <int VEC>
 __global__ void __launch_bounds__(128)
-marginal_bwd_prep_kernel(const float* __restrict__ V, float* __restrict__ TV, float* __restrict__ A,
-                         const float* __restrict__ nu, const float* __restrict__ g_mean,
-                         const float* __restrict__ g_var, const float* __restrict__ theta, int64_t theta_rs,
-                         int64_t D, int64_t C, int64_t P, int64_t B, float jitter,
-                         float* __restrict__ Vbar, float* __restrict__ theta_bar) {
+marginal_bwd_prep_kernel(const float* __restrict__ V, const float* NV, const float* __restrict__ nu,
+                         const float* __restrict__ g_mean, const float* __restrict__ g_var,
+                         const float* __restrict__ theta, int64_t theta_rs, int64_t D, int64_t C, int64_t P,
+                         int64_t B, float* Vbar, float* __restrict__ Vg, float* __restrict__ theta_bar) {
   __shared__ float scratch[32];
   const int64_t g = blockIdx.z;
-  const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  const int64_t p0 = (int64_t)blockIdx.y * kPrepPch, p1 = min(P, p0 + kPrepPch);
+  const int64_t b = ((int64_t)blockIdx.x * 128 + threadIdx.x) * VEC;
+  const int64_t p0 = (int64_t)blockIdx.y * kPrepPch;
+  const int rows = (int)min((int64_t)kPrepPch, P - p0);
   const bool live = b < B;
-  const float gm = live ? g_mean[g * B + b] : 0.f;
-  const float gv = live ? g_var[g * B + b] : 0.f;
+  float gm[VEC], gv[VEC];
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) gm[u] = gv[u] = 0.f;
   if (live) {
-    const float two_gv = 2.f * gv, eps_gv = 2.f * jitter * gv;
-    for (int64_t p = p0; p < p1; ++p) {
-      const int64_t o = (g * P + p) * B + b;
-      Vbar[o] = fmaf(__ldg(nu + g * P + p), gm, -two_gv * V[o]);
-      A[o] *= eps_gv;
-      TV[o] *= two_gv;
+    if (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(g_mean + g * B + b);
+      const float4 c = *reinterpret_cast<const float4*>(g_var + g * B + b);
+      gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w;
+      gv[0] = c.x; gv[1] = c.y; gv[2] = c.z; gv[3] = c.w;
+    } else {
+      gm[0] = g_mean[g * B + b];
+      gv[0] = g_var[g * B + b];
+    }
+    float vv[kPrepPch][VEC], nn[kPrepPch][VEC];
+#pragma unroll
+    for (int r = 0; r < kPrepPch; ++r) {
+      if (r < rows) {
+        const int64_t o = (g * P + p0 + r) * B + b;
+        if (VEC == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(V + o);
+          const float4 c = *reinterpret_cast<const float4*>(NV + o);
+          vv[r][0] = a.x; vv[r][1] = a.y; vv[r][2] = a.z; vv[r][3] = a.w;
+          nn[r][0] = c.x; nn[r][1] = c.y; nn[r][2] = c.z; nn[r][3] = c.w;
+        } else {
+          vv[r][0] = V[o];
+          nn[r][0] = NV[o];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kPrepPch; ++r) {
+      if (r < rows) {
+        const int64_t o = (g * P + p0 + r) * B + b;
+        const float nur = __ldg(nu + g * P + p0 + r);
+        float vb[VEC], vg[VEC];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+          vb[u] = fmaf(nur, gm[u], 2.f * gv[u] * (nn[r][u] - vv[r][u]));
+          vg[u] = gv[u] * vv[r][u];
+        }
+        if (VEC == 4) {
+          *reinterpret_cast<float4*>(Vbar + o) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+          *reinterpret_cast<float4*>(Vg + o) = make_float4(vg[0], vg[1], vg[2], vg[3]);
+        } else {
+          Vbar[o] = vb[0];
+          Vg[o] = vg[0];
+        }
+      }
     }
   }
   if (blockIdx.y == 0) {
-    const float s = block_sum(gv, scratch);
+    float t = 0.f;
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) t += gv[u];
+    const float s = block_sum(t, scratch);
     if (threadIdx.x == 0) {
       const int64_t h = g / C;
       atomicAdd(theta_bar + h * (D + 1) + D, 2.f * expf(2.f * theta[h * theta_rs + D]) * s);
@@ -65,15 +121,34 @@ marginal_bwd_prep_kernel(const float* __restrict__ V, float* __restrict__ TV, fl
   }
 }
 
-// X <- (Phi(X) + Phi(X)^T)/2 : Xi_ij = Xi_ji = X_ij / 2 for i >= j
-__global__ void sym_phi_kernel(float* __restrict__ X, int64_t n) {
+// mirror == 0: X <- (Phi(X) + Phi(X)^T)/2, i.e. Xi_ij = Xi_ji = X_ij / 2 for i >= j;  mirror != 0: X_ji <- X_ij (i >= j)
+// grid (tile column bj, tile row bi >= bj, batch), 32 x 32 tiles through shared memory so that both the lower tile
+// and its mirror image are written with full 128 B lines.
+__global__ void __launch_bounds__(256)
+sym_phi_kernel(float* __restrict__ X, int64_t n, float scale) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
   float* x = X + (int64_t)blockIdx.z * n * n;
-  const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
-  if (i >= n || j >= n || j > i) return;
-  const float v = 0.5f * x[i * n + j];
-  x[i * n + j] = v;
-  x[j * n + i] = v;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int64_t i0 = (int64_t)bi * 32, j0 = (int64_t)bj * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = i0 + r, j = j0 + tx;
+    float v = 0.f;
+    if (i < n && j < n && j <= i) {
+      v = scale * x[i * n + j];
+      x[i * n + j] = v;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    // mirrored element (row j0 + r, col i0 + tx) = lower element (i0 + tx, j0 + r)
+    const int64_t jj = j0 + r, ii = i0 + tx;
+    if (ii < n && jj < n && jj < ii) x[jj * n + ii] = tile[tx][r];
+  }
 }
 
 // KL(u) forward, two deterministic stages (bit-reproducible: no float atomics):
@@ -184,37 +259,46 @@ __global__ void tril_unpack_bwd_kernel(const float* __restrict__ Lbar, const flo
 
 using namespace vargp;
 
-extern "C" int vargp_marginal_reduce(const float* V, const float* TV, const float* A, const float* nu,
-                                     const float* theta, int64_t theta_rs, int64_t D, int64_t H, int64_t C,
-                                     int64_t P, int64_t B, float jitter, float* f_mean, float* f_var,
-                                     void* stream) {
-  if (!V || !TV || !A || !nu || !theta || !f_mean || !f_var) return VARGP_ERR_ARG;
+extern "C" int vargp_marginal_reduce(const float* V, const float* NV, const float* nu, const float* theta,
+                                     int64_t theta_rs, int64_t D, int64_t H, int64_t C, int64_t P, int64_t B,
+                                     float* f_mean, float* f_var, void* stream) {
+  if (!V || !NV || !nu || !theta || !f_mean || !f_var) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)(H * C));
-  marginal_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V, TV, A, nu, theta, theta_rs, D, C, P, B, jitter,
-                                                                  f_mean, f_var);
+  marginal_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, theta, theta_rs, D, C, P, B, f_mean, f_var);
   return launch_status();
 }
 
-extern "C" int vargp_marginal_bwd_prep(const float* V, float* TV, float* A, const float* nu, const float* g_mean,
+extern "C" int vargp_marginal_bwd_prep(const float* V, const float* NV, const float* nu, const float* g_mean,
                                        const float* g_var, const float* theta, int64_t theta_rs, int64_t D,
-                                       int64_t H, int64_t C, int64_t P, int64_t B, float jitter, float* Vbar,
+                                       int64_t H, int64_t C, int64_t P, int64_t B, float* Vbar, float* Vg,
                                        float* theta_bar, void* stream) {
-  if (!V || !TV || !A || !nu || !g_mean || !g_var || !theta || !Vbar || !theta_bar) return VARGP_ERR_ARG;
+  if (!V || !NV || !nu || !g_mean || !g_var || !theta || !Vbar || !Vg || !theta_bar) return VARGP_ERR_ARG;
+  if (Vg == V || Vg == NV || Vbar == V) return VARGP_ERR_ARG;
   if (H * C > 65535 || ceil_div(P, kPrepPch) > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
-  dim3 grid((unsigned)ceil_div(B, 128), (unsigned)ceil_div(P, kPrepPch), (unsigned)(H * C));
-  marginal_bwd_prep_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V, TV, A, nu, g_mean, g_var, theta, theta_rs, D,
-                                                                    C, P, B, jitter, Vbar, theta_bar);
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(NV) |
+                         reinterpret_cast<uintptr_t>(Vbar) | reinterpret_cast<uintptr_t>(Vg) |
+                         reinterpret_cast<uintptr_t>(g_mean) | reinterpret_cast<uintptr_t>(g_var);
+  if (B % 4 == 0 && bits % 16 == 0) {
+    dim3 grid((unsigned)ceil_div(B, 512), (unsigned)ceil_div(P, kPrepPch), (unsigned)(H * C));
+    marginal_bwd_prep_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
+                                                                         P, B, Vbar, Vg, theta_bar);
+  } else {
+    dim3 grid((unsigned)ceil_div(B, 128), (unsigned)ceil_div(P, kPrepPch), (unsigned)(H * C));
+    marginal_bwd_prep_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
+                                                                         P, B, Vbar, Vg, theta_bar);
+  }
   return launch_status();
 }
 
-extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, void* stream) {
+extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, int mirror, void* stream) {
   if (!X || n < 1 || batch < 1) return VARGP_ERR_ARG;
   if (batch > 65535) return VARGP_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 8), (unsigned)batch);
-  sym_phi_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(X, n);
+  if (ceil_div(n, 32) > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32), (unsigned)batch);
+  sym_phi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, mirror ? 1.f : 0.5f);
   return launch_status();
 }
 

@@ -10,9 +10,10 @@ Z = [z_0; ...; z_t] (P = (t+1) M rows) and K = K_h(Z, Z) + eps I:
                                              Choleskys of var_gp/vargp.py:61-80,108,155)
     T_s = W_ss Lu_s ,  nu_s = W_ss m_s       whitened variational factor / mean: the autoregressive joint
                                              of var_gp/gp_utils.py:101-147 is block-diagonal here
-    V   = W Kzx ,  a = W^T V
+    V   = W Kzx ,  N = blockdiag(T_s T_s^T) + eps W W^T   (P x P, symmetric, once per step)
     f_mean_b = nu . V_b
-    f_var_b  = gamma^2 - |V_b|^2 + sum_s |T_s^T V_sb|^2 + eps |a_b|^2        (gp_utils.py:150-191)
+    f_var_b  = gamma^2 - |V_b|^2 + V_b^T N V_b                                (gp_utils.py:150-191)
+             = gamma^2 - |V_b|^2 + sum_s |T_s^T V_sb|^2 + eps |W^T V_b|^2
     KL_hc    = -sum_{i in t} log W_ii - sum_i log Lu_t,ii + (|T_t|_F^2 + |nu_t|^2 - M) / 2
     kl_u     = (1/H) sum_hc KL_hc                                             (vargp.py:182-190)
 
@@ -96,16 +97,21 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
     ops.kl_fwd(W, T, nu, Lu_all[S - 1], M, kl)
 
   # (6) predictive marginal                                                    [gp_utils.py:150-191]
-  V, TV, A = new(H, C, P, B), new(H, C, P, B), new(H, C, P, B)
+  #     N = blockdiag(T_s T_s^T) + eps W W^T collects everything quadratic in V, so the minibatch-sized work is
+  #     two GEMMs (V, N V) and one streaming reduction instead of three GEMMs here and four more in the backward
+  N = new(H, C, P, P)
+  ops.gemm(W, W.transpose(-1, -2), N, alpha=JITTER, a_tri='lower', b_tri='upper', tag='N=eps*W*Wt', zeroed=True)
+  ops.gemm(T, T.transpose(-1, -2), _blocks(N, S, M), beta=1., a_tri='lower', b_tri='upper', tag='N+=T*Tt',
+           zeroed=True)
+  V, NV = new(H, C, P, B), new(H, C, P, B)
   ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx', zeroed=True)
-  ops.gemm(T.transpose(-1, -2), _rows(V, S, M), _rows(TV, S, M), a_tri='upper', tag='TV=Tt*V', zeroed=True)
-  ops.gemm(W.transpose(-1, -2), V, A, a_tri='upper', tag='A=Wt*V', zeroed=True)
+  ops.gemm(N, V, NV, tag='NV=N*V')
   f_mean, f_var = new(H, C, B), new(H, C, B)
-  ops.marginal_reduce(V, TV, A, nu, theta, JITTER, f_mean, f_var)
+  ops.marginal_reduce(V, NV, nu, theta, f_mean, f_var)
 
   if ctx is not None:
     ctx.dims = (H, C, P, B, D, S, M)
-    ctx.saved = dict(theta=theta, zs=zs4, xs=xs, Kzz=Kzz, Kzx=Kzx, W=W, T=T, nu=nu, V=V, TV=TV, A=A,
+    ctx.saved = dict(theta=theta, zs=zs4, xs=xs, Kzz=Kzz, Kzx=Kzx, W=W, T=T, nu=nu, V=V, NV=NV,
                      m_all=m_all, Lu_all=Lu_all)
   return f_mean, f_var, kl, info, L
 
@@ -119,7 +125,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   H, C, P, B, D, S, M = ctx.dims
   sv = ctx.saved
   theta, zs, xs, Kzz, Kzx, W, T, nu = (sv[k] for k in ('theta', 'zs', 'xs', 'Kzz', 'Kzx', 'W', 'T', 'nu'))
-  V, TV, A, m_all, Lu_all = (sv[k] for k in ('V', 'TV', 'A', 'm_all', 'Lu_all'))
+  V, NV, m_all, Lu_all = (sv[k] for k in ('V', 'NV', 'm_all', 'Lu_all'))
   dev, dt = V.device, V.dtype
   new = lambda *s: torch.empty(*s, device=dev, dtype=dt)
   zeros = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
@@ -139,21 +145,22 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     if g_var is None:
       g_var = torch.zeros_like(g_mean)
     g_mean, g_var = g_mean.contiguous(), g_var.contiguous()
-    # Vbar = nu gm^T - 2 V gv ; A <- 2 eps gv A ; TV <- 2 gv TV           (A, TV overwritten in place)
-    # theta_bar[:, D] += 2 gamma^2 sum_cb gv      (direct gamma^2 term of f_var)
-    Vbar = new(H, C, P, B)
-    ops.marginal_bwd_prep(V, TV, A, nu, g_mean, g_var, theta, JITTER, Vbar, theta_bar)
-    ops.gemm(T, _rows(TV, S, M), _rows(Vbar, S, M), beta=1., a_tri='lower', tag='Vbar+=T*TVg', zeroed=True)
-    ops.gemm(W, A, Vbar, beta=1., a_tri='lower', tag='Vbar+=W*Abar', zeroed=True)
+    # Vbar = nu gm^T + 2 gv (N V - V)  (overwrites NV) ;  Vg = gv V ;  theta_bar[:, D] += 2 gamma^2 sum_cb gv
+    Vbar, Vg = NV, new(H, C, P, B)
+    ops.marginal_bwd_prep(V, NV, nu, g_mean, g_var, theta, Vbar, Vg, theta_bar)
     # Kzx_bar = W^T Vbar
     Kxbar = new(H, C, P, B)
     ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
-    # Wbar = tril(Vbar Kzx^T + V Abar^T)
+    # Wbar = tril(Vbar Kzx^T)
     ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
-    ops.gemm(V, A.transpose(-1, -2), Wbar, beta=1., c_tri='lower', tag='Wbar+=V*Abart')
-    # Tbar_s = V_s TVg_s^T ; nubar = V gm
-    # (only the lower triangle of Tbar is ever consumed: T = W_ss Lu_s is lower triangular)
-    ops.gemm(_rows(V, S, M), _rows(TV, S, M).transpose(-1, -2), Tbar, c_tri='lower', tag='Tbar=Vs*TVgt')
+    # Nbar = G = sum_b gv_b V_b V_b^T (symmetric: lower triangle by GEMM, then mirrored)
+    G = new(H, C, P, P)
+    ops.gemm(Vg, V.transpose(-1, -2), G, c_tri='lower', tag='G=Vg*Vt')
+    ops.sym_phi(G, mirror=True)
+    # N = blockdiag(T_s T_s^T) + eps W W^T  =>  Tbar_s = tril(2 G_ss T_s),  Wbar += tril(2 eps G W)
+    ops.gemm(_blocks(G, S, M), T, Tbar, alpha=2., b_tri='lower', c_tri='lower', tag='Tbar=2*Gss*T', zeroed=True)
+    ops.gemm(G, W, Wbar, alpha=2. * JITTER, beta=1., b_tri='lower', c_tri='lower', tag='Wbar+=2eps*G*W', zeroed=True)
+    # nubar = V gm
     ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
   if g_kl is not None:
     # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block

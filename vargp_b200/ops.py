@@ -71,10 +71,9 @@ def _load():
   lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_kl_bwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_kl_bwd_lu.argtypes = [vp, vp, i64, i64, vp, vp]
-  lib.vargp_marginal_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, ctypes.c_float, vp, vp, vp]
-  lib.vargp_marginal_bwd_prep.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64,
-                                          ctypes.c_float, vp, vp, vp]
-  lib.vargp_sym_phi.argtypes = [vp, i64, i64, vp]
+  lib.vargp_marginal_reduce.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp]
+  lib.vargp_marginal_bwd_prep.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_sym_phi.argtypes = [vp, i64, i64, ctypes.c_int, vp]
   lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
@@ -394,25 +393,26 @@ class CudaOps:
                                          self._stream(Lu_t)), 'kl_bwd_lu')
 
   # -- predictive marginal --------------------------------------------------------------------
-  def marginal_reduce(self, V, TV, A, nu, theta, jitter, f_mean, f_var):
+  def marginal_reduce(self, V, NV, nu, theta, f_mean, f_var):
     H, C, P, B = V.shape
     _f32(theta, 'theta', contiguous=False)
     self._check(self.lib.vargp_marginal_reduce(
-      _f32(V, 'V'), _f32(TV, 'TV'), _f32(A, 'A'), _f32(nu, 'nu'), theta.data_ptr(), theta.stride(0),
-      theta.shape[1] - 1, H, C, P, B, float(jitter), _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'),
+      _f32(V, 'V'), _f32(NV, 'NV'), _f32(nu, 'nu'), theta.data_ptr(), theta.stride(0),
+      theta.shape[1] - 1, H, C, P, B, _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'),
       self._stream(V)), 'marginal_reduce')
 
-  def marginal_bwd_prep(self, V, TV, A, nu, g_mean, g_var, theta, jitter, Vbar, theta_bar):
+  def marginal_bwd_prep(self, V, NV, nu, g_mean, g_var, theta, Vbar, Vg, theta_bar):
     H, C, P, B = V.shape
     _f32(theta, 'theta', contiguous=False)
     self._check(self.lib.vargp_marginal_bwd_prep(
-      _f32(V, 'V'), _f32(TV, 'TV'), _f32(A, 'A'), _f32(nu, 'nu'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'),
-      theta.data_ptr(), theta.stride(0), theta.shape[1] - 1, H, C, P, B, float(jitter), _f32(Vbar, 'Vbar'),
+      _f32(V, 'V'), _f32(NV, 'NV'), _f32(nu, 'nu'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'),
+      theta.data_ptr(), theta.stride(0), theta.shape[1] - 1, H, C, P, B, _f32(Vbar, 'Vbar'), _f32(Vg, 'Vg'),
       _f32(theta_bar, 'theta_bar'), self._stream(V)), 'marginal_bwd_prep')
 
-  def sym_phi(self, X):
+  def sym_phi(self, X, mirror=False):
     n = X.shape[-1]
-    self._check(self.lib.vargp_sym_phi(_f32(X, 'X'), n, X.numel() // (n * n), self._stream(X)), 'sym_phi')
+    self._check(self.lib.vargp_sym_phi(_f32(X, 'X'), n, X.numel() // (n * n), int(bool(mirror)), self._stream(X)),
+                'sym_phi')
 
   # -- likelihood -----------------------------------------------------------------------------
   def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var):
