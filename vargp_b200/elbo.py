@@ -21,6 +21,8 @@ Z = [z_0; ...; z_t] (P = (t+1) M rows) and K = K_h(Z, Z) + eps I:
 ``vargp_b200.gp_utils``).  All O(P^2 B) and O(P^3) work is expressed as batched GEMMs so it can run on
 the tensor cores; nothing of size B x B is ever formed.
 """
+import os
+
 import torch
 
 from . import ops as _ops_mod
@@ -35,6 +37,44 @@ def _ops():
 class _Ctx:
   """Plain container for tensors saved between forward and backward."""
   pass
+
+
+_SIDE = {}
+USE_SIDE_STREAM = os.environ.get('VARGP_STREAMS', '1') != '0'
+
+
+class _Fork:
+  """`with fork:` queues the enclosed launches on a side stream, ordered after everything already queued on the
+  current stream; `fork.join()` makes the current stream wait for them.  The 30-matrix Cholesky and the chain of
+  P x P adjoint GEMMs leave most SMs idle, so the minibatch-sized Kzx branch runs beside them (both branches are
+  captured into the step's CUDA graph as parallel paths).  Rules that keep the caching allocator safe: every tensor
+  the side branch touches is allocated on the main stream BEFORE the fork and stays referenced until after join()."""
+
+  def __init__(self, dev):
+    self.side = None
+    if USE_SIDE_STREAM and dev.type == 'cuda':
+      key = dev.index if dev.index is not None else torch.cuda.current_device()
+      if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+      self.side = _SIDE[key]
+    self._ctx = None
+
+  def __enter__(self):
+    if self.side is not None:
+      self.side.wait_stream(torch.cuda.current_stream())
+      self._ctx = torch.cuda.stream(self.side)
+      self._ctx.__enter__()
+    return self
+
+  def __exit__(self, *exc):
+    if self._ctx is not None:
+      self._ctx.__exit__(*exc)
+      self._ctx = None
+    return False
+
+  def join(self):
+    if self.side is not None:
+      torch.cuda.current_stream().wait_stream(self.side)
 
 
 def _blocks(mat, S, M):
@@ -68,14 +108,17 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   # (1) scaled operands and their squared norms                               [kernels.py:41-44,50]
   zs, zn = new(H, C * P, D), new(H, C * P)
   xs, xn = new(H, B, D), new(H, B)
+  Kzz, Kzx = new(H, C, P, P), new(H, C, P, B)
   ops.scale_rows(Zcat.reshape(C * P, D), theta, zs, zn)
-  ops.scale_rows(x, theta, xs, xn)
   zs4, zn3 = zs.view(H, C, P, D), zn.view(H, C, P)
 
   # (2) Gram matrices                                                          [kernels.py:45-56]
-  Kzz, Kzx = new(H, C, P, P), new(H, C, P, B)
+  #     the x side and Kzx (minibatch-sized) run on the side stream next to Kzz -> Cholesky -> whitening -> KL -> N
+  fork = _Fork(dev)
+  with fork:
+    ops.scale_rows(x, theta, xs, xn)
+    ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
   ops.rbf_gram(zs4, zn3, zs4, zn3, theta, Kzz, True, tag='Kzz')
-  ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
 
   # (3) W = chol(Kzz + eps I)^-1                                               [gp_utils.py:5-11]
   L, W = new(H, C, P, P), new(H, C, P, P)
@@ -104,6 +147,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   ops.gemm(T, T.transpose(-1, -2), _blocks(N, S, M), beta=1., a_tri='lower', b_tri='upper', tag='N+=T*Tt',
            zeroed=True)
   V, NV = new(H, C, P, B), new(H, C, P, B)
+  fork.join()
   ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx', zeroed=True)
   ops.gemm(N, V, NV, tag='NV=N*V')
   f_mean, f_var = new(H, C, B), new(H, C, B)
@@ -137,7 +181,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   Wbar = zeros(H, C, P, P)
   Tbar = zeros(H, C, S, M, M)
   nubar = zeros(H, C, P)
-  Kxbar = None
+  Kxbar = Gz1 = Gx = r1 = csum = None
+  fork = _Fork(dev)
   have_data = g_mean is not None or g_var is not None
   if have_data:
     if g_mean is None:
@@ -148,9 +193,16 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     # Vbar = nu gm^T + 2 gv (N V - V)  (overwrites NV) ;  Vg = gv V ;  theta_bar[:, D] += 2 gamma^2 sum_cb gv
     Vbar, Vg = NV, new(H, C, P, B)
     ops.marginal_bwd_prep(V, NV, nu, g_mean, g_var, theta, Vbar, Vg, theta_bar)
-    # Kzx_bar = W^T Vbar
-    Kxbar = new(H, C, P, B)
-    ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
+    # Kzx side of the adjoint on the side stream: Kzx_bar = W^T Vbar -> (.) Kzx, row / column sums -> Gz1 = Wk1 xs
+    Kxbar, Gz1 = new(H, C, P, B), new(H, C, P, D)
+    Gx = new(H, C, B, D) if need_x_grad else None
+    r1, csum = zeros(H, C, P), zeros(H, B)
+    with fork:
+      ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
+      ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
+      ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
+      if need_x_grad:
+        ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
     # Wbar = tril(Vbar Kzx^T)
     ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
     # Nbar = G = sum_b gv_b V_b V_b^T (symmetric: lower triangle by GEMM, then mirrored)
@@ -192,21 +244,12 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   ops.gemm(W.transpose(-1, -2), Y, Kzzbar, alpha=-1., a_tri='upper', tag='Kzzbar=-Wt*Y', zeroed=True)
 
   # RBF adjoint                                                                 
-  r1, r2 = zeros(H, C, P), new(H, C, P)
-  csum = zeros(H, B)
-  dg = new(H, C, P)
+  r2, dg = new(H, C, P), new(H, C, P)
   ops.rbf_bwd_prep(Kzzbar, Kzz, r2, None, dg)                   # Kzzbar <- Kzzbar * Kzz (diag -> dg) ; row sums
   Gz2 = new(H, C, P, D)
   ops.gemm(Kzzbar, zs, Gz2, tag='Gz2=Wk2*zs')
-  Gz1 = Gx = None
-  if have_data:
-    ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                      # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
-    Gz1 = new(H, C, P, D)
-    ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
-    if need_x_grad:
-      Gx = new(H, C, B, D)
-      ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
   Z_bar = new(C, P, D)
+  fork.join()
   ops.rbf_bwd_finish(zs, Gz1, Gz2, r1, r2, theta, Z_bar, theta_bar, dg)
   x_bar = None
   if have_data:
