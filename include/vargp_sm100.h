@@ -108,6 +108,11 @@ int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W, int64_t w_
 int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                    float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                    int32_t* info, void* stream);
+/* Shared-memory-resident variant for n <= 128 (one CTA per matrix; potrf_small.cu): the whole factorisation of the
+ * first tasks and the diagonal-block step of vargp_chol_inv.  A may alias W.  Pivot reporting as vargp_chol_ex. */
+int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                         float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                         int32_t* info, int64_t info_base, int accumulate, void* stream);
 /* block size (multiple of 32; 0 keeps it) and minimum n (< 0 keeps it) of the blocked path;
  * returns (min_n << 32) | block after the update. */
 int64_t vargp_chol_config(int64_t block, int64_t min_n);

@@ -143,7 +143,8 @@ def test_chol_reports_non_pd(cuda_ops):
 
 
 @pytest.mark.parametrize('n,batch,nb', [(600, 4, 128), (1024, 3, 128), (450, 5, 64), (520, 2, 96), (2048, 2, 128),
-                                        (300, 6, 0), (129, 3, 128), (1000, 2, 256)])
+                                        (300, 6, 0), (129, 3, 128), (1000, 2, 256), (300, 30, 128), (128, 5, 128),
+                                        (60, 30, 128), (97, 3, 128), (1, 2, 128), (33, 4, 128), (20, 7, 128)])
 def test_chol_inv_blocked(cuda_ops, n, batch, nb):
   """vargp_chol_inv: GEMM-driven blocked factorisation + inverse (potrf_blocked.cu) incl. ragged block counts;
   nb = 0 is the small-matrix route through the one-CTA kernels."""

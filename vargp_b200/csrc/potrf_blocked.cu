@@ -23,6 +23,9 @@
 #include "common.cuh"
 
 extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
+extern "C" int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                                    float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                                    int32_t* info, int64_t info_base, int accumulate, void* stream);
 
 namespace vargp {
 
@@ -53,7 +56,8 @@ zero_upper_kernel(float* __restrict__ L, int64_t ld, int64_t bs, int n, int nb) 
 }
 
 static int g_blk_nb = 128;        // diagonal block size of the blocked factorisation
-static int g_blk_min_n = 448;     // matrices at least this large take the blocked path
+static bool g_no_small = false;   // VARGP_CHOL_NO_SMALL=1: diagonal blocks through the chol.cu kernels (A/B timing)
+static int g_blk_min_n = 129;     // matrices at least this large take the blocked path (n <= 128: potrf_small.cu)
 
 static int gemm_any(vargp_gemm_t& g, cudaStream_t s) {
   int rc = vargp_gemm_tc(&g, s);
@@ -92,8 +96,12 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     if (e) vargp_chol_config(atoll(e), -1);
     e = getenv("VARGP_CHOL_MIN_N");
     if (e) vargp_chol_config(0, atoll(e));
+    e = getenv("VARGP_CHOL_NO_SMALL");
+    if (e) g_no_small = atoi(e) != 0;
   }
   const int nb = g_blk_nb;
+  if (n <= 128 && !g_no_small)       // whole matrix fits the shared-memory kernel
+    return vargp_chol_inv_small(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, 0, 0, stream);
   if (n < g_blk_min_n || n <= nb) {
     int rc = vargp_chol(A, a_ld, a_bs, L, l_ld, l_bs, n, batch, jitter, info, stream);
     if (rc) return rc;
@@ -120,12 +128,18 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
       rc = gemm_any(g, s);
       if (rc) return rc;
     }
-    // (ii) diagonal block factor, first failing pivot of the whole matrix wins
-    rc = vargp_chol_ex(Wkk, w_ld, w_bs, Lkk, l_ld, l_bs, kb, batch, 0.f, info, k0, k0 > 0 ? 1 : 0, stream);
-    if (rc) return rc;
-    // (iii) its inverse, in place of the consumed block of W
-    rc = vargp_trtri(Lkk, l_ld, l_bs, Wkk, w_ld, w_bs, kb, batch, stream);
-    if (rc) return rc;
+    // (ii) diagonal block factor (first failing pivot of the whole matrix wins) and (iii) its inverse, in place of
+    //      the consumed block of W: one shared-memory kernel for blocks up to 128, else the one-CTA kernels
+    if (kb <= 128 && !g_no_small) {
+      rc = vargp_chol_inv_small(Wkk, w_ld, w_bs, Lkk, l_ld, l_bs, Wkk, w_ld, w_bs, kb, batch, 0.f, info, k0,
+                                k0 > 0 ? 1 : 0, stream);
+      if (rc) return rc;
+    } else {
+      rc = vargp_chol_ex(Wkk, w_ld, w_bs, Lkk, l_ld, l_bs, kb, batch, 0.f, info, k0, k0 > 0 ? 1 : 0, stream);
+      if (rc) return rc;
+      rc = vargp_trtri(Lkk, l_ld, l_bs, Wkk, w_ld, w_bs, kb, batch, stream);
+      if (rc) return rc;
+    }
     if (k0 + kb < n) {                              // (iv) L[k0+kb:, k0:k0+kb] = W[k0+kb:, k0:k0+kb] Wkk^T
       vargp_gemm_t g = gemm_desc(batch);
       g.A = W + (k0 + kb) * w_ld + k0; g.a_rs = w_ld; g.a_cs = 1; g.a_bs[1] = w_bs;
