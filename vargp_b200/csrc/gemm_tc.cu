@@ -175,17 +175,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float4* al = reinterpret_cast<float4*>(sA_lo + s * TC_TILE_BYTES);
       float4* bh = reinterpret_cast<float4*>(sB_hi + s * TC_TILE_BYTES);
       float4* bl = reinterpret_cast<float4*>(sB_lo + s * TC_TILE_BYTES);
-#pragma unroll
+      // kind::tf32 ignores the 13 low mantissa bits, so the RAW slab is the `hi` operand as it landed; only
+      // lo = x - trunc_tf32(x) is written (8 B instead of 12 B of shared-memory traffic per element)
+#pragma unroll 4
       for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
         const int idx = e * 128 + t;
-        float4 v = ah[idx], h, l;
-        h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-        ah[idx] = h; al[idx] = l;
-        v = bh[idx];
-        h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-        bh[idx] = h; bl[idx] = l;
+        const float4 va = ah[idx], vb = bh[idx];
+        float4 l;
+        l.x = tf32_lo_of(va.x); l.y = tf32_lo_of(va.y); l.z = tf32_lo_of(va.z); l.w = tf32_lo_of(va.w);
+        al[idx] = l;
+        l.x = tf32_lo_of(vb.x); l.y = tf32_lo_of(vb.y); l.z = tf32_lo_of(vb.z); l.w = tf32_lo_of(vb.w);
+        bl[idx] = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
       __syncwarp();
@@ -241,25 +241,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       drain(t_row + 2u * TC_BN);
     }
-    if (m < p.M) {
+    // ---- store.  After the drain a thread owns ROW m and 64 consecutive columns; stored like that, each store
+    //      instruction of a warp touches 32 different rows (ncu: long-scoreboard stalls on the beta read-modify-write
+    //      and 32 sectors per request).  Row-major C: every 32 x 32 block is transposed through a padded per-warp
+    //      tile carved out of the (now idle: all MMAs have retired) operand ring, so that a lane owns a COLUMN and a
+    //      warp writes one 128 B line per instruction, eight rows in flight.  Other layouts keep lanes along m. ----
+    {
+      float* tile_f = reinterpret_cast<float*>(smem) + (warp - 6) * (32 * 33);
+      const uint32_t tile = smem_u32(tile_f);
+      const int Mi = (int)p.M, Ni = (int)p.N;
+      const int mrow = (int)m0 + quad * 32;
+      const bool rbf = p.epi != VARGP_EPI_NONE, sym = p.epi == VARGP_EPI_RBF_SYM;
+      const bool row_major = p.c_cs == 1;
+      const bool accum = p.beta != 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int64_t n = n0 + half * 64 + j;
-        if (n >= p.N) break;
-        const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m);
-        float* cp = Cb + m * p.c_rs + n * p.c_cs;
-        if (masked) {
-          if (p.beta == 0.f) *cp = 0.f;
-          continue;
+      for (int c = 0; c < 2; ++c) {
+        const int nc0 = (int)n0 + half * 64 + c * 32;
+        if (nc0 >= Ni || mrow >= Mi) break;                                    // warp-uniform
+        if (row_major) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile + 4u * (lane * 33 + j)), "f"(acc[c * 32 + j] - rown) : "memory");
+          __syncwarp();
+          const int n = nc0 + lane;
+          const bool n_ok = n < Ni;
+          float coln = 0.f;
+          if (rbf && n_ok) coln = 0.5f * e_col[n];
+          float* cp0 = Cb + (int64_t)mrow * p.c_rs + n;
+#pragma unroll 1
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            if (mrow + r0 >= Mi) break;
+            float xv[8], cv[8];
+            bool ok[8], masked[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int mm = mrow + r0 + u;
+              ok[u] = n_ok && mm < Mi;
+              masked[u] = (p.tri_c == VARGP_TRI_LOWER && n > mm) || (p.tri_c == VARGP_TRI_UPPER && n < mm);
+              cv[u] = 0.f;
+              if (accum && ok[u] && !masked[u]) cv[u] = cp0[(int64_t)(r0 + u) * p.c_rs];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[u]) : "r"(tile + 4u * ((r0 + u) * 33 + lane)));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (rbf) {
+                xv[u] = gamma2 * expf(xv[u] - coln);
+                if (sym && mrow + r0 + u == n) xv[u] = gamma2;
+              }
+              xv[u] *= p.alpha;
+              if (accum) xv[u] = fmaf(p.beta, cv[u], xv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float* cp = cp0 + (int64_t)(r0 + u) * p.c_rs;
+              if (accum) {
+                if (ok[u] && !masked[u]) *cp = xv[u];
+              } else if (ok[u]) {
+                *cp = masked[u] ? 0.f : xv[u];
+              }
+            }
+          }
+        } else if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t n = nc0 + j;
+            if (n >= p.N) break;
+            const bool masked = (p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m);
+            float* cp = Cb + m * p.c_rs + n * p.c_cs;
+            if (masked) {
+              if (p.beta == 0.f) *cp = 0.f;
+              continue;
+            }
+            float v = acc[c * 32 + j];
+            if (rbf) {
+              v = gamma2 * expf(v - rown - 0.5f * e_col[n]);
+              if (sym && m == n) v = gamma2;
+            }
+            v *= p.alpha;
+            if (p.beta != 0.f) v = fmaf(p.beta, *cp, v);
+            *cp = v;
+          }
         }
-        float v = acc[j];
-        if (p.epi != VARGP_EPI_NONE) {
-          v = gamma2 * expf(v - rown - 0.5f * e_col[n]);
-          if (p.epi == VARGP_EPI_RBF_SYM && m == n) v = gamma2;
-        }
-        v *= p.alpha;
-        if (p.beta != 0.f) v = fmaf(p.beta, *cp, v);
-        *cp = v;
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

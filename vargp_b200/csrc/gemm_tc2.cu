@@ -94,12 +94,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// x -> (hi, lo): hi = x truncated to tf32 (what the tensor core sees when it is fed x itself), lo = x - hi rounded to
-// tf32 (round-half-up on the magnitude, 2 integer ops: left to the hardware, lo would be TRUNCATED, a one-sided error)
-__device__ __forceinline__ float tf32_lo_of(float x) {
-  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

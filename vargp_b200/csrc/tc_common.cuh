@@ -92,6 +92,13 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// x -> (hi, lo): hi = x truncated to tf32 (what the tensor core sees when it is fed x itself), lo = x - hi rounded to
+// tf32 (round-half-up on the magnitude, 2 integer ops: left to the hardware, lo would be TRUNCATED, a one-sided error)
+__device__ __forceinline__ float tf32_lo_of(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
