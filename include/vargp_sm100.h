@@ -179,6 +179,17 @@ int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps,
 int vargp_softmax_predict(const float* f_mean, const float* f_var, const float* eps,
                           int64_t H, int64_t F, int64_t C, int64_t B, float* probs, void* stream);
 
+/* Kernel hyper-parameters (var_gp/kernels.py:62-77), H samples of D1 = D + 1 log-hyper-parameters:
+ *   theta[h][d] = log_mean[d] + exp(log_logvar[d] / 2) * eps[h][d]                 (Normal.rsample)
+ *   kl[0] = sum_d KL( N(log_mean, exp(log_logvar)) || N(prior_log_mean, exp(prior_log_logvar)) )   (kl may be NULL)
+ * and the adjoint given theta_bar (H, D1) and the scalar g_kl on the device (either may be NULL). */
+int vargp_hyper_fwd(const float* log_mean, const float* log_logvar, const float* prior_log_mean,
+                    const float* prior_log_logvar, const float* eps, int64_t H, int64_t D1, float* theta, float* kl,
+                    void* stream);
+int vargp_hyper_bwd(const float* log_mean, const float* log_logvar, const float* prior_log_mean,
+                    const float* prior_log_logvar, const float* eps, const float* theta_bar, const float* g_kl,
+                    int64_t H, int64_t D1, float* log_mean_bar, float* log_logvar_bar, void* stream);
+
 /* Fused Yogi step over a flat parameter buffer (the optimizer the reference trains with,
  * experiments/vargp.py:23): m <- b1 m + (1-b1) g;  v <- v - (1-b2) sign(v - g^2) g^2;
  * p <- p - lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps).  pows = {b1^t, b2^t} lives on the device and is

@@ -157,6 +157,22 @@ class EmuOps:
     f = f_mean.unsqueeze(1) + f_var.sqrt().unsqueeze(1) * eps_f
     probs.copy_(torch.softmax(f, dim=-2).sum((0, 1)).T / (H * F))
 
+  def hyper_fwd(self, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta, kl):
+    theta.copy_(log_mean + torch.exp(0.5 * log_logvar) * eps)
+    if kl is not None:
+      dl, dm = log_logvar - prior_log_logvar, log_mean - prior_log_mean
+      kl.copy_((0.5 * (dl.exp() + dm * dm * torch.exp(-prior_log_logvar) - 1. - dl)).sum())
+
+  def hyper_bwd(self, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta_bar, g_kl, m_bar, lv_bar):
+    m_bar.zero_()
+    lv_bar.zero_()
+    if theta_bar is not None:
+      m_bar += theta_bar.sum(0)
+      lv_bar += 0.5 * torch.exp(0.5 * log_logvar) * (theta_bar * eps).sum(0)
+    if g_kl is not None:
+      m_bar += g_kl * (log_mean - prior_log_mean) * torch.exp(-prior_log_logvar)
+      lv_bar += 0.5 * g_kl * (torch.exp(log_logvar - prior_log_logvar) - 1.)
+
   def yogi_step(self, p, g, m, v, lr, b1, b2, eps, pows):
     pows[0] *= b1
     pows[1] *= b2

@@ -35,6 +35,16 @@ class GradBucket:
         p.grad.copy_(v)
 
 
-def shard_loss(kl_hypers, kl_u, nll_local, beta, n_data, global_batch, world_size):
-  """Per-rank loss whose gradients SUM (over ranks) to the gradient of the full-batch ELBO."""
-  return (beta * kl_hypers + kl_u) / world_size + (n_data / global_batch) * nll_local
+def shard_coef(beta, n_data, global_batch, world_size):
+  """Coefficients of (kl_hypers, kl_u, nll_local) in the per-rank loss."""
+  return (beta / world_size, 1.0 / world_size, n_data / global_batch)
+
+
+def shard_loss(kl_hypers, kl_u, nll_local, beta, n_data, global_batch, world_size, coef=None):
+  """Per-rank loss whose gradients SUM (over ranks) to the gradient of the full-batch ELBO.
+  With `coef` (a device tensor holding `shard_coef(...)`) the combination is one fused autograd node."""
+  if coef is not None:
+    from .functional import Combine3Fn
+    return Combine3Fn.apply(kl_hypers, kl_u, nll_local, coef)
+  a, b, c = shard_coef(beta, n_data, global_batch, world_size)
+  return a * kl_hypers + b * kl_u + c * nll_local

@@ -21,6 +21,7 @@ Z = [z_0; ...; z_t] (P = (t+1) M rows) and K = K_h(Z, Z) + eps I:
 ``vargp_b200.gp_utils``).  All O(P^2 B) and O(P^3) work is expressed as batched GEMMs so it can run on
 the tensor cores; nothing of size B x B is ever formed.
 """
+import math
 import os
 
 import torch
@@ -77,6 +78,17 @@ class _Fork:
       torch.cuda.current_stream().wait_stream(self.side)
 
 
+def _zeros_many(dev, dt, *shapes):
+  """Zero-filled tensors of the given shapes carved out of ONE buffer (one fill launch; 128 B aligned segments)."""
+  sizes = [math.prod(sh) for sh in shapes]
+  offs, tot = [], 0
+  for n in sizes:
+    offs.append(tot)
+    tot += (n + 31) // 32 * 32
+  flat = torch.zeros(tot, device=dev, dtype=dt)
+  return [flat[o:o + n].view(sh) for o, n, sh in zip(offs, sizes, shapes)]
+
+
 def _blocks(mat, S, M):
   """(H, C, P, P) -> view (H, C, S, M, M) of the S diagonal M x M blocks (no copy)."""
   H, C, P, _ = mat.shape
@@ -122,7 +134,11 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
 
   # (3) W = chol(Kzz + eps I)^-1                                               [gp_utils.py:5-11]
   L, W = new(H, C, P, P), new(H, C, P, P)
-  info = torch.zeros(H * C, device=dev, dtype=torch.int32)
+  if dt == torch.float32:       # Cholesky status words and the KL accumulator share one zero-filled buffer
+    zb = torch.zeros(H * C + 1, device=dev, dtype=dt)
+    info, kl0 = zb[:H * C].view(torch.int32), zb[H * C]
+  else:
+    info, kl0 = torch.zeros(H * C, device=dev, dtype=torch.int32), torch.zeros((), device=dev, dtype=dt)
   ops.chol_inv(Kzz, L, W, JITTER, info)
 
   # (4) whitened variational parameters (block diagonal)
@@ -136,7 +152,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None):
   # (5) KL(q(u_t | u_<t) || p(u_t | u_<t))                                     [vargp.py:182-190]
   kl = None
   if want_kl:
-    kl = torch.zeros((), device=dev, dtype=dt)
+    kl = kl0
     ops.kl_fwd(W, T, nu, Lu_all[S - 1], M, kl)
 
   # (6) predictive marginal                                                    [gp_utils.py:150-191]
@@ -177,10 +193,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M)
   mB = m_all.permute(1, 0, 2).unsqueeze(0)                      # (1, C, S, M)
 
-  theta_bar = zeros(H, D + 1)
-  Wbar = zeros(H, C, P, P)
-  Tbar = zeros(H, C, S, M, M)
-  nubar = zeros(H, C, P)
+  Wbar, Tbar, nubar, theta_bar, r1z, csumz = _zeros_many(dev, dt, (H, C, P, P), (H, C, S, M, M), (H, C, P), (H, D + 1),
+                                                         (H, C, P), (H, B))
   Kxbar = Gz1 = Gx = r1 = csum = None
   fork = _Fork(dev)
   have_data = g_mean is not None or g_var is not None
@@ -196,7 +210,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     # Kzx side of the adjoint on the side stream: Kzx_bar = W^T Vbar -> (.) Kzx, row / column sums -> Gz1 = Wk1 xs
     Kxbar, Gz1 = new(H, C, P, B), new(H, C, P, D)
     Gx = new(H, C, B, D) if need_x_grad else None
-    r1, csum = zeros(H, C, P), zeros(H, B)
+    r1, csum = r1z, csumz
     with fork:
       ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
@@ -223,13 +237,15 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   ops.gemm(Tbar, LuB.transpose(-1, -2), Wbd, beta=1., a_tri='lower', b_tri='upper', c_tri='lower', tag='whiten_adj',
            zeroed=True)
   ops.gemm(nubar.view(H, C, S, M, 1), mB.unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
-  Lubar_h = new(H, C, S, M, M)
-  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h, a_tri='upper', b_tri='lower', c_tri='lower', tag='whiten_adj',
-           zeroed=True)
-  mbar_h = new(H, C, S, M, 1)
-  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h, a_tri='upper', tag='whiten_adj', zeroed=True)
-  Lu_bar = Lubar_h.sum(0).permute(1, 0, 2, 3).contiguous()      # (S, C, M, M)
-  m_bar = mbar_h.sum(0).squeeze(-1).permute(1, 0, 2).contiguous()
+  #   (the per-h products are written task-major, so that the sum over h is already in parameter layout)
+  Lubar_h = new(H, S, C, M, M)
+  ops.gemm(Wd.transpose(-1, -2), Tbar, Lubar_h.permute(0, 2, 1, 3, 4), a_tri='upper', b_tri='lower', c_tri='lower',
+           tag='whiten_adj', zeroed=True)
+  mbar_h = new(H, S, C, M, 1)
+  ops.gemm(Wd.transpose(-1, -2), nubar.view(H, C, S, M, 1), mbar_h.permute(0, 2, 1, 3, 4), a_tri='upper',
+           tag='whiten_adj', zeroed=True)
+  Lu_bar = Lubar_h.sum(0)                                        # (S, C, M, M)
+  m_bar = mbar_h.sum(0).squeeze(-1)                              # (S, C, M)
   if g_kl is not None:
     # d/dLu_t of -sum_i log Lu_t,ii  (mean over h of H identical terms)
     ops.kl_bwd_lu(Lu_all[S - 1], g_kl, Lu_bar[S - 1])

@@ -63,6 +63,46 @@ class TrilUnpackFn(torch.autograd.Function):
     return gv, None
 
 
+class HyperFn(torch.autograd.Function):
+  """(log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps) -> (theta (H, D+1), kl_hypers): the
+  reparameterised hyper sample and KL(q(theta) || p(theta)) of var_gp/kernels.py:62-77, one launch forward and one
+  backward instead of ~30 elementwise launches."""
+
+  @staticmethod
+  def forward(ctx, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps):
+    lm, lv = log_mean.detach().contiguous(), log_logvar.detach().contiguous()
+    pm, plv, eps = prior_log_mean.detach().contiguous(), prior_log_logvar.detach().contiguous(), eps.contiguous()
+    theta = torch.empty_like(eps)
+    kl = torch.empty((), device=eps.device, dtype=eps.dtype)
+    _ops().hyper_fwd(lm, lv, pm, plv, eps, theta, kl)
+    ctx.save_for_backward(lm, lv, pm, plv, eps)
+    ctx.set_materialize_grads(False)
+    return theta, kl
+
+  @staticmethod
+  def backward(ctx, g_theta, g_kl):
+    lm, lv, pm, plv, eps = ctx.saved_tensors
+    m_bar, lv_bar = torch.empty_like(lm), torch.empty_like(lv)
+    _ops().hyper_bwd(lm, lv, pm, plv, eps, None if g_theta is None else g_theta.contiguous(),
+                     None if g_kl is None else g_kl.detach().reshape(1).contiguous(), m_bar, lv_bar)
+    return m_bar, lv_bar, None, None, None
+
+
+class Combine3Fn(torch.autograd.Function):
+  """loss = coef . (kl_hypers, kl_u, nll)  (experiments/vargp.py:34) with 3 launches for forward + backward."""
+
+  @staticmethod
+  def forward(ctx, kl_h, kl_u, nll, coef):
+    ctx.save_for_backward(coef)
+    return torch.dot(torch.stack((kl_h.detach(), kl_u.detach(), nll.detach())), coef)
+
+  @staticmethod
+  def backward(ctx, g):
+    coef, = ctx.saved_tensors
+    g3 = g * coef
+    return g3[0], g3[1], g3[2], None
+
+
 class SoftmaxNllFn(torch.autograd.Function):
   """(f_mean, f_var, y, eps) -> nll; forward and adjoint come out of one kernel pass
   (var_gp/likelihoods.py:13-47)."""
@@ -71,15 +111,16 @@ class SoftmaxNllFn(torch.autograd.Function):
   def forward(ctx, f_mean, f_var, y, eps):
     f_mean, f_var = f_mean.detach().contiguous(), f_var.detach().contiguous()
     nll = torch.zeros((), device=f_mean.device, dtype=f_mean.dtype)
-    gm, gv = torch.empty_like(f_mean), torch.empty_like(f_var)
-    _ops().nll_fwd_bwd(f_mean, f_var, eps.contiguous(), y.contiguous(), nll, gm, gv)
-    ctx.save_for_backward(gm, gv)
+    gmv = torch.empty((2,) + tuple(f_mean.shape), device=f_mean.device, dtype=f_mean.dtype)
+    _ops().nll_fwd_bwd(f_mean, f_var, eps.contiguous(), y.contiguous(), nll, gmv[0], gmv[1])
+    ctx.save_for_backward(gmv)
     return nll
 
   @staticmethod
   def backward(ctx, g):
-    gm, gv = ctx.saved_tensors
-    return gm * g, gv * g, None, None
+    gmv, = ctx.saved_tensors
+    gmv = gmv * g                       # one launch for both adjoints
+    return gmv[0], gmv[1], None, None
 
 
 def softmax_predict(f_mean, f_var, eps):

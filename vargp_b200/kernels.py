@@ -134,6 +134,17 @@ class RBFKernel(nn.Module):
                         device=self.log_mean.device).normal_()
     return self.log_mean + self.log_logvar.exp().sqrt() * eps
 
+  def sample_hypers_with_kl(self, n_hypers, eps=None):
+    """(theta, kl_hypers) from ONE fused launch (+ one for the backward); same draw and same values as
+    `sample_hypers` followed by `kl_hypers`."""
+    if self.map_est:
+      return self.sample_hypers(n_hypers, eps), self.kl_hypers()
+    if eps is None:
+      eps = torch.empty((n_hypers,) + self.log_mean.shape, dtype=self.log_mean.dtype,
+                        device=self.log_mean.device).normal_()
+    from .functional import HyperFn
+    return HyperFn.apply(self.log_mean, self.log_logvar, self.prior_log_mean, self.prior_log_logvar, eps)
+
   def kl_hypers(self):
     """sum_{D+1} KL(N(m_q, s_q^2) || N(m_p, s_p^2))   (var_gp/kernels.py:70-77; 785 elements: stays PyTorch)."""
     if self.map_est:

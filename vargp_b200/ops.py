@@ -80,6 +80,8 @@ def _load():
   lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
   lib.vargp_yogi_step.argtypes = [vp, vp, vp, vp, i64] + [ctypes.c_float] * 4 + [vp, vp]
+  lib.vargp_hyper_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
+  lib.vargp_hyper_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
   return lib
 
 
@@ -127,7 +129,7 @@ class CudaOps:
   # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
   _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'chol_inv', 'tril_unpack',
                  'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'marginal_reduce', 'marginal_bwd_prep',
-                 'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step')
+                 'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step', 'hyper_fwd', 'hyper_bwd')
 
   def profile_start(self):
     """Bracket every launch with CUDA events (slows the host side; never on during a timed region)."""
@@ -429,6 +431,24 @@ class CudaOps:
       _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), H, F, C, B, _f32(probs, 'probs'),
       self._stream(f_mean)), 'softmax_predict')
 
+
+  # -- kernel hyper-parameters ----------------------------------------------------------------
+  def hyper_fwd(self, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta, kl):
+    H, D1 = eps.shape
+    self._check(self.lib.vargp_hyper_fwd(_f32(log_mean, 'log_mean'), _f32(log_logvar, 'log_logvar'),
+                                         _f32(prior_log_mean, 'prior_log_mean'),
+                                         _f32(prior_log_logvar, 'prior_log_logvar'), _f32(eps, 'eps'), H, D1,
+                                         _f32(theta, 'theta'), None if kl is None else _f32(kl, 'kl'),
+                                         self._stream(theta)), 'hyper_fwd')
+
+  def hyper_bwd(self, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta_bar, g_kl, m_bar, lv_bar):
+    H, D1 = eps.shape
+    self._check(self.lib.vargp_hyper_bwd(_f32(log_mean, 'log_mean'), _f32(log_logvar, 'log_logvar'),
+                                         _f32(prior_log_mean, 'prior_log_mean'),
+                                         _f32(prior_log_logvar, 'prior_log_logvar'), _f32(eps, 'eps'),
+                                         None if theta_bar is None else _f32(theta_bar, 'theta_bar'),
+                                         None if g_kl is None else _f32(g_kl, 'g_kl'), H, D1,
+                                         _f32(m_bar, 'm_bar'), _f32(lv_bar, 'lv_bar'), self._stream(m_bar)), 'hyper_bwd')
 
   # -- optimizer ------------------------------------------------------------------------------
   def yogi_step(self, p, g, m, v, lr, b1, b2, eps, pows):

@@ -12,7 +12,7 @@ device buffers before each replay; the three loss terms come back in static 0-d 
 import torch
 import torch.distributed as dist
 
-from .dist import shard_loss
+from .dist import shard_coef, shard_loss
 from .optim import FlatYogi
 
 
@@ -27,6 +27,7 @@ class ElboStepper:
     D = gp.z.size(-1) if not hasattr(gp.kernel, 'phi') else gp.kernel.phi[0].in_features
     self.x = torch.empty(batch_size, D, device=dev)
     self.y = torch.empty(batch_size, dtype=torch.int64, device=dev)
+    self.coef = torch.tensor(shard_coef(beta, n_data, self.global_batch, world_size), device=dev)
     self.terms = None
     self.launches_per_step = None
     gp.sync_errors = False
@@ -34,7 +35,7 @@ class ElboStepper:
   def _body(self):
     self.opt.zero_grad()
     kl_h, kl_u, nll = self.gp.loss(self.x, self.y)
-    loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world)
+    loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
     loss.backward()
     if self.world > 1:
       dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)

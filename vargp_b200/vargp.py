@@ -127,7 +127,7 @@ class VARGP(nn.Module):
     if self.var_mean_mask != 1.0:
       from .composed import loss_composed
       return loss_composed(self, x, y, noise)
-    theta = self.kernel.sample_hypers(self.n_v, eps=noise.get('eps_theta'))
+    theta, kl_hypers = self.kernel.sample_hypers_with_kl(self.n_v, eps=noise.get('eps_theta'))
     f_mean, f_var, kl_u, _ = self._marginal(x, theta, want_kl=True)
     if self.n_prev and 'eps_u' not in noise:
       # the reference draws u_<t here (vargp.py:138); with ep_var_mean=True the KL does not depend on it
@@ -135,7 +135,6 @@ class VARGP(nn.Module):
       torch.empty((self.n_v, theta.size(0), self.z.size(0), self.n_prev * self.M),
                   dtype=self.z.dtype, device=self.z.device).normal_()
     nll = self.likelihood.loss(f_mean, f_var, y, eps=noise.get('eps_f'))
-    kl_hypers = self.kernel.kl_hypers()
     return kl_hypers, kl_u, nll
 
   def predict(self, x, noise=None):
