@@ -75,6 +75,10 @@ int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
  * vargp_tc2_launch_count: launches of that kernel since load. */
 int64_t vargp_tc2_config(int64_t min_tiles);
 int64_t vargp_tc2_launch_count(void);
+/* profiling aid: CTA (0,0,0) of every following 1-CTA vargp_gemm_tc launch writes 8 clock64() stamps of its pipeline
+ * (entry, setup, first slab landed, first slab issued, first partial sum, MMAs retired, stored, exit) to `buf`
+ * (device memory, >= 8 int64); NULL switches it off. */
+void vargp_tc_debug(long long* buf);
 
 /* dst[h][r][:] = src[r][:] * exp(-theta[h][:D]);  norms[h][r] = |dst[h][r]|^2.
  * Replaces the `x / sigma` broadcasts and the Gram diagonals of var_gp/kernels.py:41-44,50-51,54. */

@@ -27,6 +27,7 @@ struct TcParams {
   int64_t e_theta_bs[3], e_D;
   int32_t a_mn, b_mn;            // 1: operand is M/N-contiguous (MN-major), 0: K-contiguous
   int32_t a_b[3], b_b[3];        // 1 if the operand really varies along that batch dim (else coordinate 0)
+  long long* dbg;                // optional: 8 clock64() stamps of CTA 0's pipeline (vargp_tc_debug; profiling only)
 };
 
 // ---------------------------------------------------------------------------------------------
