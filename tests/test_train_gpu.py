@@ -51,3 +51,30 @@ def test_graphed_step_trains_like_eager(cuda_ops):
     assert all(torch.isfinite(p).all() for p in gp.parameters())
   assert abs(res[True][1] - res[False][1]) < 0.2 * abs(res[False][1])   # different RNG streams
   assert st.launches_per_step and st.launches_per_step < 80
+
+
+def test_train_driver_continual_toy(cuda_ops):
+  """vargp_b200.train.train (experiments/vargp.py:14-73 restated): two toy tasks through create_clf -> graphed
+  steps -> on-device evaluation -> early stopper; the returned state dicts carry the reference's keys, feed the
+  next task as prev_params and reload through create_clf + load_state_dict (the notebooks' protocol)."""
+  from vargp_b200.train import TensorTask, train, compute_accuracy, compute_acc_ent, compute_bwt
+  from vargp_b200.vargp import VARGP
+  g = torch.Generator().manual_seed(0)
+  centers = torch.tensor([[-1., -1.], [1., 1.], [-1., 1.], [1., -1.]])
+  y = torch.arange(4).repeat_interleave(60)
+  x = centers[y] + 0.4 * torch.randn(240, 2, generator=g)
+  tasks = [TensorTask.for_classes(x, y, c) for c in ((0, 1), (2, 3))]
+  torch.manual_seed(1)
+  prev, accs = [], []
+  for t, ds in enumerate(tasks):
+    sd = train(t, ds, ds, ds, epochs=60, M=12, lr=3e-2, eval_interval=20, patience=5, prev_params=prev,
+               batch_size=64, device='cuda')
+    assert set(sd) >= {'z', 'u_mean', 'u_tril_vec', 'kernel.log_mean', 'kernel.log_logvar'}
+    assert sd['z'].shape == (4, 12, 2)                        # all four output GPs exist from task 0 (vargp.py:204)
+    gp = VARGP.create_clf(ds, M=12, prev_params=prev).cuda()
+    gp.load_state_dict(sd)
+    prev.append(sd)
+    accs.append([compute_accuracy(d, gp) for d in tasks])
+  acc, ent = compute_acc_ent(TensorTask(x, y), gp)
+  assert accs[0][0] > 0.8 and accs[1][1] > 0.8 and acc > 0.6 and ent > 0
+  assert compute_bwt(torch.tensor(accs)).abs() < 0.5

@@ -70,3 +70,155 @@ class ElboStepper:
       self._capture()      # note: the capture itself does not advance the parameters
     self.graph.replay()
     return self.terms
+
+
+# ------------------------------------------------------------------------------------------------------
+# Training / evaluation driver: the per-task loop of experiments/vargp.py:14-73 and the
+# helpers of var_gp/train_utils.py:21-98, restated for device-resident data -- tensors instead of Dataset/DataLoader
+# objects, the graph-replayed ElboStepper as the inner loop, accuracies accumulated on the device (one host sync
+# per evaluation instead of one per batch).  Logging (wandb / tensorboard) and checkpoint files stay with the caller.
+# ------------------------------------------------------------------------------------------------------
+class TensorTask:
+  """Device-friendly stand-in for the reference's datasets (var_gp/datasets.py:70-138): `data` (N, D) and `targets`
+  (N,) hold the WHOLE benchmark, `task_ids` (optional index tensor) selects the items of the current task -- like
+  SplitMNIST, whose `targets` stay unfiltered, which is why create_clf sizes the model for every class from task 0
+  on (var_gp/vargp.py:204).  Indexing returns (x, y) of the selected items; `.x` / `.y` are the selected tensors."""
+
+  def __init__(self, data, targets, task_ids=None):
+    self.data, self.targets, self.task_ids = data, targets, task_ids
+
+  @classmethod
+  def for_classes(cls, data, targets, classes):
+    mask = torch.zeros_like(targets, dtype=torch.bool)
+    for c in classes:
+      mask |= targets == c
+    return cls(data, targets, mask.nonzero().squeeze(-1))
+
+  @property
+  def x(self):
+    return self.data if self.task_ids is None else self.data[self.task_ids]
+
+  @property
+  def y(self):
+    return self.targets if self.task_ids is None else self.targets[self.task_ids]
+
+  def __len__(self):
+    return self.data.size(0) if self.task_ids is None else self.task_ids.numel()
+
+  def __getitem__(self, idx):
+    if self.task_ids is not None:
+      idx = self.task_ids[idx]
+    return self.data[idx], self.targets[idx]
+
+
+@torch.no_grad()
+def compute_accuracy(dataset, gp, batch_size=512, device=None, noise_fn=None):
+  """var_gp/train_utils.py:21-35.  `noise_fn(i, B)` may pin the predictive noise of batch i."""
+  device = device or gp.z.device
+  correct = torch.zeros((), dtype=torch.int64, device=device)
+  n, xs, ys = len(dataset), dataset.x, dataset.y
+  for i, lo in enumerate(range(0, n, batch_size)):
+    x, y = xs[lo:lo + batch_size].to(device), ys[lo:lo + batch_size].to(device)
+    preds = gp.predict(x, noise=None if noise_fn is None else noise_fn(i, x.size(0)))
+    correct += (preds.argmax(dim=-1) == y).sum()
+  return correct.item() / n
+
+
+@torch.no_grad()
+def compute_acc_ent(dataset, gp, batch_size=512, device=None):
+  """var_gp/train_utils.py:38-56: mean accuracy and mean predictive entropy."""
+  device = device or gp.z.device
+  correct = torch.zeros((), dtype=torch.int64, device=device)
+  ent = torch.zeros((), device=device)
+  n, xs, ys = len(dataset), dataset.x, dataset.y
+  for lo in range(0, n, batch_size):
+    x, y = xs[lo:lo + batch_size].to(device), ys[lo:lo + batch_size].to(device)
+    preds = gp.predict(x)
+    if torch.isnan(preds).any():
+      raise AssertionError('Found NaNs')
+    correct += (preds.argmax(dim=-1) == y).sum()
+    ent += -(preds * preds.clamp_min(1e-38).log()).sum()
+  return correct.item() / n, ent.item() / n
+
+
+def compute_bwt(acc_mat):
+  """Backward transfer (var_gp/train_utils.py:59-66): mean over earlier tasks of final minus just-trained accuracy."""
+  acc_mat = torch.as_tensor(acc_mat)
+  if acc_mat.ndim != 2 or acc_mat.shape[0] != acc_mat.shape[1]:
+    raise AssertionError('acc_mat must be square')
+  return (acc_mat[-1][:-1] - acc_mat.diagonal()[:-1]).mean()
+
+
+class EarlyStopper:
+  """var_gp/train_utils.py:70-98 (same counter / delta semantics)."""
+
+  def __init__(self, patience=10, delta=1e-4):
+    self.patience, self.delta = patience, delta
+    self._counter, self._best_info, self._best_score = 0, None, None
+
+  def is_done(self):
+    return self.patience >= 0 and self._counter >= self.patience
+
+  def info(self):
+    return self._best_info
+
+  def __call__(self, score, info):
+    if self.is_done():
+      raise AssertionError('stopper is done')
+    if self._best_score is None:
+      self._best_score, self._best_info = score, info
+    elif score < self._best_score + self.delta:
+      self._counter += 1
+    else:
+      self._best_score, self._best_info, self._counter = score, info, 0
+
+
+def snapshot_state(gp):
+  """Detached copy of the state dict (the reference keeps aliases of the live parameters, so its "best" checkpoint
+  is in fact the latest one -- SURVEY.md section 5; here the best really is the best)."""
+  return {k: v.detach().clone() for k, v in gp.state_dict().items()}
+
+
+def train(task_id, train_set, val_set, test_set, ep_var_mean=True, map_est_hypers=False, dkl=False, epochs=1, M=20,
+          n_f=10, n_var_samples=3, batch_size=512, lr=1e-2, beta=1.0, eval_interval=10, patience=20,
+          prev_params=None, logger=None, device=None, use_graph=True):
+  """experiments/vargp.py:14-73 with the same keyword arguments.  Returns the best state dict (by validation
+  accuracy), which the caller appends to `prev_params` for the next task."""
+  from .vargp import VARGP
+  device = torch.device(device or 'cuda')
+  gp = VARGP.create_clf(train_set, M=M, n_f=n_f, n_var_samples=n_var_samples, prev_params=prev_params,
+                        ep_var_mean=ep_var_mean, map_est_hypers=map_est_hypers, dkl=dkl).to(device)
+  stopper = EarlyStopper(patience=patience)
+  N = len(train_set)
+  xs, ys = train_set.x.to(device), train_set.y.to(device)
+  fused = ep_var_mean and not dkl
+  steppers = {}                      # one captured graph per batch size (the last batch of an epoch is short)
+
+  def stepper_for(B):
+    if B not in steppers:
+      opt = steppers[next(iter(steppers))].opt if steppers else None
+      steppers[B] = ElboStepper(gp, n_data=N, batch_size=B, beta=beta, lr=lr, use_graph=use_graph and fused,
+                                optimizer=opt)
+    return steppers[B]
+
+  terms = None
+  for e in range(epochs):
+    perm = torch.randperm(N, device=device)                 # DataLoader(shuffle=True)
+    for lo in range(0, N, batch_size):
+      idx = perm[lo:lo + batch_size]
+      terms = stepper_for(idx.numel()).step(xs[idx], ys[idx])
+    if (e + 1) % eval_interval == 0:
+      gp.check_errors()
+      acc = {k: compute_accuracy(d, gp, device=device) for k, d in (('train', train_set), ('val', val_set),
+                                                                    ('test', test_set))}
+      summary = {f'task{task_id}/{k}/acc': v for k, v in acc.items()}
+      summary.update({f'task{task_id}/loss/{k}': float(v) for k, v in zip(('kl_hypers', 'kl_u', 'lik'), terms)})
+      if logger is not None:
+        for k, v in summary.items():
+          logger.add_scalar(k, v, global_step=e + 1)
+      stopper(acc['val'], dict(state_dict=snapshot_state(gp), acc_summary=summary, step=e + 1))
+      if stopper.is_done():
+        break
+  gp.check_errors()
+  info = stopper.info()
+  return info['state_dict'] if info is not None else snapshot_state(gp)
