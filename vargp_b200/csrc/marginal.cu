@@ -122,18 +122,19 @@ marginal_bwd_prep_kernel(const float* __restrict__ V, const float* NV, const flo
 }
 
 // mirror == 0: X <- (Phi(X) + Phi(X)^T)/2, i.e. Xi_ij = Xi_ji = X_ij / 2 for i >= j;  mirror != 0: X_ji <- X_ij (i >= j)
-// grid (tile column bj, tile row bi >= bj, batch), 32 x 32 tiles through shared memory so that both the lower tile
+// grid (tile column bj, tile row bi >= bj, batch), 64 x 64 tiles through shared memory so that both the lower tile
 // and its mirror image are written with full 128 B lines.
+constexpr int kSymT = 64;
 __global__ void __launch_bounds__(256)
 sym_phi_kernel(float* __restrict__ X, int64_t n, float scale) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[kSymT][kSymT + 1];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj > bi) return;
   float* x = X + (int64_t)blockIdx.z * n * n;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  const int64_t i0 = (int64_t)bi * 32, j0 = (int64_t)bj * 32;
-#pragma unroll
-  for (int r = ty; r < 32; r += 8) {
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+  const int64_t i0 = (int64_t)bi * kSymT, j0 = (int64_t)bj * kSymT;
+#pragma unroll 4
+  for (int r = ty; r < kSymT; r += 4) {
     const int64_t i = i0 + r, j = j0 + tx;
     float v = 0.f;
     if (i < n && j < n && j <= i) {
@@ -143,8 +144,8 @@ sym_phi_kernel(float* __restrict__ X, int64_t n, float scale) {
     tile[r][tx] = v;
   }
   __syncthreads();
-#pragma unroll
-  for (int r = ty; r < 32; r += 8) {
+#pragma unroll 4
+  for (int r = ty; r < kSymT; r += 4) {
     // mirrored element (row j0 + r, col i0 + tx) = lower element (i0 + tx, j0 + r)
     const int64_t jj = j0 + r, ii = i0 + tx;
     if (ii < n && jj < n && jj < ii) x[jj * n + ii] = tile[tx][r];
@@ -296,8 +297,8 @@ extern "C" int vargp_marginal_bwd_prep(const float* V, const float* NV, const fl
 extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, int mirror, void* stream) {
   if (!X || n < 1 || batch < 1) return VARGP_ERR_ARG;
   if (batch > 65535) return VARGP_ERR_UNSUPPORTED;
-  if (ceil_div(n, 32) > 65535) return VARGP_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32), (unsigned)batch);
+  if (ceil_div(n, kSymT) > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(n, kSymT), (unsigned)ceil_div(n, kSymT), (unsigned)batch);
   sym_phi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, mirror ? 1.f : 0.5f);
   return launch_status();
 }
