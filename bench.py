@@ -293,6 +293,10 @@ def run_gpu(args):
     return
 
   pk = peaks()
+  traffic = {}
+  tpath = os.path.join(ROOT, 'profiles', 'r1b_traffic.json')       # per-launch DRAM bytes from the committed ncu captures
+  if os.path.exists(tpath):
+    traffic = {k: v.get('bytes_per_launch') for k, v in json.load(open(tpath)).items() if isinstance(v, dict)}
   by_kernel = {}
   for tag, d in prof.items():
     k = by_kernel.setdefault(d['kernel'], dict(ms=0.0, flops=0.0, bytes=0.0, calls=0))
@@ -305,12 +309,12 @@ def run_gpu(args):
     tf32x3_peak = pk['bf16_sustained'] / 6.0     # TF32 dense = bf16/2; 3xTF32 issues 3 MMAs per product
     ach = tk['flops'] / (tk['ms'] * 1e-3) / 1e12
     roof = dict(kernel=top, bound='tensor', achieved=round(ach, 3), peak=round(tf32x3_peak, 1), unit='TFLOP/s',
-                frac=round(ach / tf32x3_peak, 4), traffic=None,
+                frac=round(ach / tf32x3_peak, 4), traffic=traffic.get('gemm_tc2' if wl == 'scaled' else top),
                 peak_note=f'3xTF32 = {pk["src"]} bf16 sustained / 6', share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
   else:
     ach = tk['bytes'] / (tk['ms'] * 1e-3) / 1e9
     roof = dict(kernel=top, bound='hbm', achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
-                frac=round(ach / pk['hbm'], 4), traffic=None, peak_note=f'{pk["src"]} copy bandwidth',
+                frac=round(ach / pk['hbm'], 4), traffic=traffic.get(top), peak_note=f'{pk["src"]} copy bandwidth',
                 share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
   value = world * K / (ms * 1e-3)
   e2e_v = world * K / (ms_e2e * 1e-3)
