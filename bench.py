@@ -199,8 +199,9 @@ def run_gpu(args):
     cfg = dict(cfg, B=args.batch)
   B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
   global_B = B * world
-  use_graph = (not args.no_graph) and (world == 1 or args.graph_multi) and wl != 'scaled'   # scaled: ~100 GB of
-  # workspaces live once in the eager allocator; a graph-private pool on top of the warm-up pool would not fit
+  # scaled: ~100 GB of workspaces live once in the eager allocator; a graph-private pool on top of the warm-up pool
+  # would not fit.  N > 1: the graph covers zero_grad .. backward, the all-reduce and the Yogi step follow eagerly.
+  use_graph = (not args.no_graph) and wl != 'scaled'
   from vargp_b200.train import ElboStepper
   stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
                         use_graph=use_graph)
@@ -384,7 +385,6 @@ def main():
   ap.add_argument('--batch', type=int, default=None, help='override the (global) minibatch size of the workload')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
-  ap.add_argument('--graph-multi', action='store_true', help='also capture the step (incl. the NCCL all-reduce) when N > 1')
   ap.add_argument('--verbose', action='store_true', help='progress lines on stderr')
   ap.add_argument('--detail', action='store_true', help='add per-call-site kernel times to the JSON line')
   args = ap.parse_args()

@@ -32,17 +32,27 @@ class ElboStepper:
     self.launches_per_step = None
     gp.sync_errors = False
 
-  def _body(self):
+  def _grad_body(self):
     self.opt.zero_grad()
     kl_h, kl_u, nll = self.gp.loss(self.x, self.y)
     loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
     loss.backward()
+    return kl_h.detach(), kl_u.detach(), nll.detach()
+
+  def _finish(self):
     if self.world > 1:
       dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
     self.opt.step()
-    return kl_h.detach(), kl_u.detach(), nll.detach()
+
+  def _body(self):
+    terms = self._grad_body()
+    self._finish()
+    return terms
 
   def _capture(self):
+    """Single GPU: the whole step is one graph.  Data parallel: the graph ends with the backward pass; the
+    all-reduce of the flat gradient buffer and the (two-launch) Yogi step follow it eagerly, which keeps NCCL out
+    of the capture at the price of three host calls per step instead of one."""
     from . import ops as _ops_mod
     ops = _ops_mod.get_ops()
     # warm up on a side stream (allocator pools, lazy inits, cuBLAS-free so nothing else to prime)
@@ -56,8 +66,8 @@ class ElboStepper:
     self.graph = torch.cuda.CUDAGraph()
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph):
-      self.terms = self._body()
-    self.launches_per_step = ops.launch_count() - n0
+      self.terms = self._grad_body() if self.world > 1 else self._body()
+    self.launches_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
 
   def step(self, x, y):
     """One optimisation step on the minibatch (x, y) (device or pinned-host tensors).  Returns the three
@@ -69,6 +79,8 @@ class ElboStepper:
     if self.graph is None:
       self._capture()      # note: the capture itself does not advance the parameters
     self.graph.replay()
+    if self.world > 1:
+      self._finish()
     return self.terms
 
 
