@@ -1,8 +1,11 @@
 // Library bookkeeping: init, version, error strings, launch counter.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vargp {
 int64_t g_launches = 0;
+bool g_pdl = true;
 int g_device = -1;
 }  // namespace vargp
 
@@ -34,5 +37,7 @@ extern "C" int vargp_init(int device) {
   if (e != cudaSuccess) return (int)e;
   if (prop.major != 10) return VARGP_ERR_UNSUPPORTED;   // sm_100a only: no other code path exists
   g_device = device;
+  const char* pdl = getenv("VARGP_PDL");
+  if (pdl) g_pdl = atoi(pdl) != 0;
   return vargp_tc_init();
 }

@@ -44,6 +44,7 @@ __device__ __forceinline__ void warp_store_rows(float* base, int64_t ld, int row
 __global__ void __launch_bounds__(kCholThreads)
 chol_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l_ld,
             int64_t l_bs, int n, float jitter, int32_t* __restrict__ info, int info_base, int accumulate) {
+  pdl_enter();
   __shared__ __align__(16) float Bs[NB][NB + 4];   // Bs[kk][c] = L[k0 + c][kc + kk]   (transposed block)
   __shared__ __align__(16) float Ds[NB][NB + 4];   // factored diagonal block, Ds[j][l] = Lkk[j][l]
   __shared__ __align__(16) float colj[NB];         // column j of the diagonal block during its factorisation
@@ -188,6 +189,7 @@ constexpr int kDiagWarps = 4;
 __global__ void __launch_bounds__(kDiagWarps * 32)
 trtri_diag_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld, int64_t w_bs, int n,
                   int nblk) {
+  pdl_enter();
   __shared__ __align__(16) float Ls[kDiagWarps][NB][NB + 4];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk = blockIdx.x * kDiagWarps + wid;
@@ -235,6 +237,7 @@ constexpr int kSweepWarps = 16;
 __global__ void __launch_bounds__(kSweepWarps * 32)
 trtri_sweep_kernel(const float* Lin, int64_t l_ld, int64_t l_bs, float* Wout, int64_t w_ld, int64_t w_bs, int n,
                    int nblk) {
+  pdl_enter();
   extern __shared__ float dyn[];
   float (*tile)[NB + 1] = reinterpret_cast<float (*)[NB + 1]>(dyn + (threadIdx.x >> 5) * NB * (NB + 1));  // per warp
   float (*red)[NB][NB + 1] = reinterpret_cast<float (*)[NB][NB + 1]>(dyn + kSweepWarps * NB * (NB + 1));  // [warp][r][c]
@@ -320,7 +323,7 @@ extern "C" int vargp_chol_ex(const float* A, int64_t a_ld, int64_t a_bs, float* 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  chol_kernel<<<(unsigned)batch, kCholThreads, dyn, (cudaStream_t)stream>>>(A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
+  launch_k(chol_kernel, dim3((unsigned)batch), dim3(kCholThreads), dyn, (cudaStream_t)stream, A, a_ld, a_bs, L, l_ld, l_bs, (int)n,
                                                                             jitter, info, (int)info_base, accumulate);
   return launch_status();
 }
@@ -337,7 +340,7 @@ extern "C" int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W,
   const int nblk = (int)ceil_div(n, NB);
   if (batch > 65535) return VARGP_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  trtri_diag_kernel<<<dim3((unsigned)ceil_div(nblk, kDiagWarps), (unsigned)batch), kDiagWarps * 32, 0, s>>>(
+  launch_k(trtri_diag_kernel, dim3(dim3((unsigned)ceil_div(nblk, kDiagWarps), (unsigned)batch)), dim3(kDiagWarps * 32), 0, s, 
       L, l_ld, l_bs, W, w_ld, w_bs, (int)n, nblk);
   int rc = launch_status();
   if (rc) return rc;
@@ -348,7 +351,7 @@ extern "C" int vargp_trtri(const float* L, int64_t l_ld, int64_t l_bs, float* W,
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  trtri_sweep_kernel<<<dim3((unsigned)nblk, (unsigned)batch), kSweepWarps * 32, dyn, s>>>(L, l_ld, l_bs, W, w_ld, w_bs,
+  launch_k(trtri_sweep_kernel, dim3(dim3((unsigned)nblk, (unsigned)batch)), dim3(kSweepWarps * 32), dyn, s, L, l_ld, l_bs, W, w_ld, w_bs,
                                                                                         (int)n, nblk);
   return launch_status();
 }

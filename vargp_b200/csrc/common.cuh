@@ -13,6 +13,35 @@ extern int64_t g_launches;   // counted on the host at every kernel launch (benc
 #define VARGP_ERR_UNSUPPORTED (-2)
 #define VARGP_ERR_NOT_INIT (-3)
 
+extern bool g_pdl;            // programmatic dependent launch between the library's kernels (VARGP_PDL=0 disables)
+
+// Every kernel of the library starts with pdl_enter(): `launch_dependents` lets the NEXT kernel of the stream (or
+// graph) be scheduled onto SMs as they drain instead of after this grid has fully retired, `wait` blocks until
+// the PREVIOUS grid has completed and its writes are visible.  Both are no-ops for launches without the
+// programmatic-serialization attribute.  The step is ~80 short dependent kernels, so the per-boundary launch
+// latency is a measurable share of it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int launch_status() {
   ++g_launches;
   cudaError_t e = cudaPeekAtLastError();

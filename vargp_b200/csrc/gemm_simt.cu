@@ -17,6 +17,7 @@ struct GemmCfg {
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(const vargp_gemm_t g) {
+  pdl_enter();
   using Cfg = GemmCfg<BM, BN, BK, TM, TN>;
   constexpr int NT = Cfg::kThreads;
   constexpr int TX = BN / TN;       // threads along n
@@ -150,6 +151,7 @@ gemm_simt_kernel(const vargp_gemm_t g) {
 // (nubar = V gm, nu = W_ss m: a 64x64 GEMM tile would waste 63/64 of its lanes.)
 __global__ void __launch_bounds__(256)
 gemv_kernel(const vargp_gemm_t g) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t m = (int64_t)blockIdx.x * 8 + wid;
   int64_t z = blockIdx.z;
@@ -196,17 +198,17 @@ extern "C" int vargp_gemm(const vargp_gemm_t* g, void* stream) {
   if (g->N == 1 && g->epi == VARGP_EPI_NONE && g->tri_b == VARGP_TRI_NONE && g->tri_c == VARGP_TRI_NONE &&
       g->a_cs <= g->a_rs && g->M >= 8) {
     dim3 grid((unsigned)ceil_div(g->M, 8), 1, (unsigned)nbatch);
-    gemv_kernel<<<grid, 256, 0, s>>>(*g);
+    launch_k(gemv_kernel, dim3(grid), dim3(256), 0, s, *g);
     return launch_status();
   }
   // large tiles only when they still fill the machine (148 SMs)
   const int64_t big_tiles = ceil_div(g->M, 128) * ceil_div(g->N, 128) * nbatch;
   if (g->M >= 128 && g->N >= 128 && big_tiles >= 148) {
     dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, 128), (unsigned)nbatch);
-    gemm_simt_kernel<128, 128, 8, 8, 8><<<grid, 256, 0, s>>>(*g);
+    launch_k((gemm_simt_kernel<128, 128, 8, 8, 8>), dim3(grid), dim3(256), 0, s, *g);
   } else {
     dim3 grid((unsigned)ceil_div(g->N, 64), (unsigned)ceil_div(g->M, 64), (unsigned)nbatch);
-    gemm_simt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, s>>>(*g);
+    launch_k((gemm_simt_kernel<64, 64, 16, 4, 4>), dim3(grid), dim3(256), 0, s, *g);
   }
   return launch_status();
 }

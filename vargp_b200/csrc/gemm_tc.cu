@@ -52,6 +52,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* lo_bar = bars + 3 * TC_STAGES + 4;    // cross-term accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 5);
 
+  pdl_launch_dependents();     // the next kernel's CTAs may be scheduled as soon as every CTA of this grid has started
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 #define TC_STAMP(i) do { if (stamp) p.dbg[i] = clock64(); } while (0)
@@ -101,6 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // barriers, TMEM and tensor maps are set up; from here on global memory is touched
   if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
@@ -411,7 +413,7 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   if (tc2_wants(g)) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
 
   dim3 grid((unsigned)ceil_div(g->N, TC_BN), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+  launch_k(gemm_tc_kernel, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
   return launch_status();
 }
 

@@ -218,6 +218,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * T2_STAGES + 4);
   float* stage_s = reinterpret_cast<float*>(bars + 32);       // [T2_EPI_WARPS][32][33] transpose tiles of the store
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int64_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
@@ -250,6 +251,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                              // peer's barriers are initialised before any remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
@@ -582,9 +584,9 @@ int tc2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p
   for (int i = 0; i < 3; ++i)
     if (p.nb[i] > 1 && p.c_bs[i] % 4 != 0) c_vec4 = 0;
   if (g_t2_rna)
-    gemm_tc2_kernel<false><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4, g_t2_dbg);
+    launch_k((gemm_tc2_kernel<false>), dim3(dim3((unsigned)(2 * ncl))), dim3(T2_THREADS), T2_SMEM_BYTES, stream, tmA, tmB, p, c_vec4, g_t2_dbg);
   else
-    gemm_tc2_kernel<true><<<dim3((unsigned)(2 * ncl)), T2_THREADS, T2_SMEM_BYTES, stream>>>(tmA, tmB, p, c_vec4, g_t2_dbg);
+    launch_k((gemm_tc2_kernel<true>), dim3(dim3((unsigned)(2 * ncl))), dim3(T2_THREADS), T2_SMEM_BYTES, stream, tmA, tmB, p, c_vec4, g_t2_dbg);
   ++g_t2_launches;
   return launch_status();
 }

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256)
 hyper_fwd_kernel(const float* __restrict__ m, const float* __restrict__ lv, const float* __restrict__ pm,
                  const float* __restrict__ plv, const float* __restrict__ eps, int64_t H, int64_t D1,
                  float* __restrict__ theta, float* __restrict__ kl) {
+  pdl_enter();
   __shared__ float scratch[32];
   float acc = 0.f;
   for (int64_t d = threadIdx.x; d < D1; d += blockDim.x) {
@@ -34,6 +35,7 @@ hyper_bwd_kernel(const float* __restrict__ m, const float* __restrict__ lv, cons
                  const float* __restrict__ plv, const float* __restrict__ eps, const float* __restrict__ theta_bar,
                  const float* __restrict__ g_kl, int64_t H, int64_t D1, float* __restrict__ m_bar,
                  float* __restrict__ lv_bar) {
+  pdl_enter();
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D1) return;
   float sm = 0.f, sl = 0.f;
@@ -64,7 +66,7 @@ extern "C" int vargp_hyper_fwd(const float* log_mean, const float* log_logvar, c
                                float* kl, void* stream) {
   if (!log_mean || !log_logvar || !eps || !theta || H < 1 || D1 < 1) return VARGP_ERR_ARG;
   if (kl && (!prior_log_mean || !prior_log_logvar)) return VARGP_ERR_ARG;
-  hyper_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, H,
+  launch_k(hyper_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, H,
                                                         D1, theta, kl);
   return launch_status();
 }
@@ -75,7 +77,7 @@ extern "C" int vargp_hyper_bwd(const float* log_mean, const float* log_logvar, c
                                void* stream) {
   if (!log_mean || !log_logvar || !eps || !log_mean_bar || !log_logvar_bar || H < 1 || D1 < 1) return VARGP_ERR_ARG;
   if (g_kl && (!prior_log_mean || !prior_log_logvar)) return VARGP_ERR_ARG;
-  hyper_bwd_kernel<<<(unsigned)ceil_div(D1, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(hyper_bwd_kernel, dim3((unsigned)ceil_div(D1, 256)), dim3(256), 0, (cudaStream_t)stream, 
       log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta_bar, g_kl, H, D1, log_mean_bar, log_logvar_bar);
   return launch_status();
 }

@@ -11,6 +11,7 @@ softmax_nll_kernel(const float* __restrict__ f_mean, const float* __restrict__ f
                    const float* __restrict__ eps, const int64_t* __restrict__ y,
                    int64_t H, int64_t F, int64_t C, int64_t B,
                    float* __restrict__ nll, float* __restrict__ g_mean, float* __restrict__ g_var) {
+  pdl_enter();
   __shared__ float scratch[32];
   const int64_t h = blockIdx.y;
   const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(128)
 softmax_predict_kernel(const float* __restrict__ f_mean, const float* __restrict__ f_var,
                        const float* __restrict__ eps, int64_t H, int64_t F, int64_t C, int64_t B,
                        float* __restrict__ probs) {
+  pdl_enter();
   const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (b >= B) return;
   float p[CMAX];
@@ -132,10 +134,10 @@ extern "C" int vargp_softmax_nll(const float* f_mean, const float* f_var, const 
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)H);
   cudaStream_t s = (cudaStream_t)stream;
-  if (C <= 4) softmax_nll_kernel<4><<<grid, 128, 0, s>>>(f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else if (C <= 10) softmax_nll_kernel<10><<<grid, 128, 0, s>>>(f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else if (C <= 16) softmax_nll_kernel<16><<<grid, 128, 0, s>>>(f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else softmax_nll_kernel<32><<<grid, 128, 0, s>>>(f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
+  if (C <= 4) launch_k((softmax_nll_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
+  else if (C <= 10) launch_k((softmax_nll_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
+  else if (C <= 16) launch_k((softmax_nll_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
+  else launch_k((softmax_nll_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
   return launch_status();
 }
 
@@ -147,9 +149,9 @@ extern "C" int vargp_softmax_predict(const float* f_mean, const float* f_var, co
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128));
   cudaStream_t s = (cudaStream_t)stream;
-  if (C <= 4) softmax_predict_kernel<4><<<grid, 128, 0, s>>>(f_mean, f_var, eps, H, F, C, B, probs);
-  else if (C <= 10) softmax_predict_kernel<10><<<grid, 128, 0, s>>>(f_mean, f_var, eps, H, F, C, B, probs);
-  else if (C <= 16) softmax_predict_kernel<16><<<grid, 128, 0, s>>>(f_mean, f_var, eps, H, F, C, B, probs);
-  else softmax_predict_kernel<32><<<grid, 128, 0, s>>>(f_mean, f_var, eps, H, F, C, B, probs);
+  if (C <= 4) launch_k((softmax_predict_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, H, F, C, B, probs);
+  else if (C <= 10) launch_k((softmax_predict_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, H, F, C, B, probs);
+  else if (C <= 16) launch_k((softmax_predict_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, H, F, C, B, probs);
+  else launch_k((softmax_predict_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, H, F, C, B, probs);
   return launch_status();
 }

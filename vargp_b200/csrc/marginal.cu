@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(128)
 marginal_reduce_kernel(const float* __restrict__ V, const float* __restrict__ NV, const float* __restrict__ nu,
                        const float* __restrict__ theta, int64_t theta_rs, int64_t D, int64_t C, int64_t P,
                        int64_t B, float* __restrict__ f_mean, float* __restrict__ f_var) {
+  pdl_enter();
   const int64_t g = blockIdx.y;
   const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (b >= B) return;
@@ -53,6 +54,7 @@ marginal_bwd_prep_kernel(const float* __restrict__ V, const float* NV, const flo
                          const float* __restrict__ g_mean, const float* __restrict__ g_var,
                          const float* __restrict__ theta, int64_t theta_rs, int64_t D, int64_t C, int64_t P,
                          int64_t B, float* Vbar, float* __restrict__ Vg, float* __restrict__ theta_bar) {
+  pdl_enter();
   __shared__ float scratch[32];
   const int64_t g = blockIdx.z;
   const int64_t b = ((int64_t)blockIdx.x * 128 + threadIdx.x) * VEC;
@@ -127,6 +129,7 @@ marginal_bwd_prep_kernel(const float* __restrict__ V, const float* NV, const flo
 constexpr int kSymT = 64;
 __global__ void __launch_bounds__(256)
 sym_phi_kernel(float* __restrict__ X, int64_t n, float scale) {
+  pdl_enter();
   __shared__ float tile[kSymT][kSymT + 1];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj > bi) return;
@@ -160,6 +163,7 @@ constexpr int kKlChunks = VARGP_KL_CHUNKS;
 __global__ void __launch_bounds__(256)
 kl_fwd_part_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
                    const float* __restrict__ Lu, int64_t C, int64_t P, int64_t M, float* __restrict__ part) {
+  pdl_enter();
   __shared__ float scratch[32];
   const int64_t g = blockIdx.y, c = g % C, S = P / M, Q = P - M;
   const float* w = W + g * P * P;
@@ -189,6 +193,7 @@ kl_fwd_part_kernel(const float* __restrict__ W, const float* __restrict__ T, con
 
 __global__ void __launch_bounds__(32)
 kl_fwd_sum_kernel(const float* __restrict__ part, int64_t n, int64_t H, float* __restrict__ kl) {
+  pdl_enter();
   float acc = 0.f;
   for (int64_t g = threadIdx.x; g < n; g += 32) acc += part[g];
   acc = warp_sum(acc);
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(256)
 kl_bwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
               const float* __restrict__ g_kl, int64_t H, int64_t C, int64_t P, int64_t M,
               float* __restrict__ Wbar, float* __restrict__ Tbar, float* __restrict__ nubar) {
+  pdl_enter();
   const int64_t g = blockIdx.y, S = P / M, Q = P - M;
   const float s = g_kl[0] / (float)H;
   const float* t = T + (g * S + (S - 1)) * M * M;
@@ -217,6 +223,7 @@ kl_bwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const fl
 
 __global__ void kl_bwd_lu_kernel(const float* __restrict__ Lu, const float* __restrict__ g_kl, int64_t C, int64_t M,
                                  float* __restrict__ Lubar) {
+  pdl_enter();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= C * M) return;
   const int64_t c = e / M, i = e % M;
@@ -230,6 +237,7 @@ __device__ __forceinline__ float softplus_f(float x) {   // torch.nn.functional.
 
 // packed row-major lower triangle -> dense, softplus on the diagonal      (gp_utils.py:22-49)
 __global__ void tril_unpack_kernel(const float* __restrict__ vec, int64_t M, float* __restrict__ out) {
+  pdl_enter();
   const int64_t c = blockIdx.z;
   const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
@@ -245,6 +253,7 @@ __global__ void tril_unpack_kernel(const float* __restrict__ vec, int64_t M, flo
 
 __global__ void tril_unpack_bwd_kernel(const float* __restrict__ Lbar, const float* __restrict__ vec, int64_t M,
                                        float* __restrict__ vec_bar) {
+  pdl_enter();
   const int64_t c = blockIdx.z;
   const int64_t j = (int64_t)blockIdx.x * 32 + threadIdx.x;
   const int64_t i = (int64_t)blockIdx.y * 8 + threadIdx.y;
@@ -267,7 +276,7 @@ extern "C" int vargp_marginal_reduce(const float* V, const float* NV, const floa
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)(H * C));
-  marginal_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, theta, theta_rs, D, C, P, B, f_mean, f_var);
+  launch_k(marginal_reduce_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, V, NV, nu, theta, theta_rs, D, C, P, B, f_mean, f_var);
   return launch_status();
 }
 
@@ -284,11 +293,11 @@ extern "C" int vargp_marginal_bwd_prep(const float* V, const float* NV, const fl
                          reinterpret_cast<uintptr_t>(g_mean) | reinterpret_cast<uintptr_t>(g_var);
   if (B % 4 == 0 && bits % 16 == 0) {
     dim3 grid((unsigned)ceil_div(B, 512), (unsigned)ceil_div(P, kPrepPch), (unsigned)(H * C));
-    marginal_bwd_prep_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
+    launch_k((marginal_bwd_prep_kernel<4>), dim3(grid), dim3(128), 0, (cudaStream_t)stream, V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
                                                                          P, B, Vbar, Vg, theta_bar);
   } else {
     dim3 grid((unsigned)ceil_div(B, 128), (unsigned)ceil_div(P, kPrepPch), (unsigned)(H * C));
-    marginal_bwd_prep_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
+    launch_k((marginal_bwd_prep_kernel<1>), dim3(grid), dim3(128), 0, (cudaStream_t)stream, V, NV, nu, g_mean, g_var, theta, theta_rs, D, C,
                                                                          P, B, Vbar, Vg, theta_bar);
   }
   return launch_status();
@@ -299,7 +308,7 @@ extern "C" int vargp_sym_phi(float* X, int64_t n, int64_t batch, int mirror, voi
   if (batch > 65535) return VARGP_ERR_UNSUPPORTED;
   if (ceil_div(n, kSymT) > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(n, kSymT), (unsigned)ceil_div(n, kSymT), (unsigned)batch);
-  sym_phi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, mirror ? 1.f : 0.5f);
+  launch_k(sym_phi_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, X, n, mirror ? 1.f : 0.5f);
   return launch_status();
 }
 
@@ -307,10 +316,10 @@ extern "C" int vargp_kl_fwd(const float* W, const float* T, const float* nu, con
                             int64_t P, int64_t M, float* kl, float* work, void* stream) {
   if (!W || !T || !nu || !Lu || !kl || !work || M < 1 || P % M) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
-  kl_fwd_part_kernel<<<dim3(kKlChunks, (unsigned)(H * C)), 256, 0, (cudaStream_t)stream>>>(W, T, nu, Lu, C, P, M, work);
+  launch_k(kl_fwd_part_kernel, dim3(dim3(kKlChunks, (unsigned)(H * C))), dim3(256), 0, (cudaStream_t)stream, W, T, nu, Lu, C, P, M, work);
   int rc = launch_status();
   if (rc) return rc;
-  kl_fwd_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(work, H * C * kKlChunks, H, kl);
+  launch_k(kl_fwd_sum_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, work, H * C * kKlChunks, H, kl);
   return launch_status();
 }
 
@@ -319,7 +328,7 @@ extern "C" int vargp_kl_bwd(const float* W, const float* T, const float* nu, con
   if (!W || !T || !nu || !g_kl || !Wbar || !Tbar || !nubar || M < 1 || P % M) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
   const unsigned chunks = (unsigned)(M < 64 ? 1 : (M / 32 > 128 ? 128 : M / 32));
-  kl_bwd_kernel<<<dim3(chunks, (unsigned)(H * C)), 256, 0, (cudaStream_t)stream>>>(W, T, nu, g_kl, H, C, P, M, Wbar,
+  launch_k(kl_bwd_kernel, dim3(dim3(chunks, (unsigned)(H * C))), dim3(256), 0, (cudaStream_t)stream, W, T, nu, g_kl, H, C, P, M, Wbar,
                                                                                    Tbar, nubar);
   return launch_status();
 }
@@ -327,7 +336,7 @@ extern "C" int vargp_kl_bwd(const float* W, const float* T, const float* nu, con
 extern "C" int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar,
                                void* stream) {
   if (!Lu || !g_kl || !Lubar) return VARGP_ERR_ARG;
-  kl_bwd_lu_kernel<<<(unsigned)ceil_div(C * M, 128), 128, 0, (cudaStream_t)stream>>>(Lu, g_kl, C, M, Lubar);
+  launch_k(kl_bwd_lu_kernel, dim3((unsigned)ceil_div(C * M, 128)), dim3(128), 0, (cudaStream_t)stream, Lu, g_kl, C, M, Lubar);
   return launch_status();
 }
 
@@ -335,7 +344,7 @@ extern "C" int vargp_tril_unpack(const float* vec, int64_t C, int64_t M, float* 
   if (!vec || !out || C < 1 || M < 1) return VARGP_ERR_ARG;
   if (C > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(M, 8), (unsigned)C);
-  tril_unpack_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(vec, M, out);
+  launch_k(tril_unpack_kernel, dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, vec, M, out);
   return launch_status();
 }
 
@@ -344,6 +353,6 @@ extern "C" int vargp_tril_unpack_bwd(const float* Lbar, const float* vec, int64_
   if (!Lbar || !vec || !vec_bar || C < 1 || M < 1) return VARGP_ERR_ARG;
   if (C > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(M, 8), (unsigned)C);
-  tril_unpack_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(Lbar, vec, M, vec_bar);
+  launch_k(tril_unpack_bwd_kernel, dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, Lbar, vec, M, vec_bar);
   return launch_status();
 }

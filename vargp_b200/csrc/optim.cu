@@ -7,6 +7,7 @@ namespace vargp {
 
 // pows[0] = beta1^t, pows[1] = beta2^t kept on the device so the step is CUDA-graph replayable
 __global__ void yogi_advance_kernel(float* pows, float b1, float b2) {
+  pdl_enter();
   pows[0] *= b1;
   pows[1] *= b2;
 }
@@ -14,6 +15,7 @@ __global__ void yogi_advance_kernel(float* pows, float b1, float b2) {
 __global__ void __launch_bounds__(256)
 yogi_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, float lr, float b1, float b2, float eps, const float* __restrict__ pows) {
+  pdl_enter();
   const float bc1 = 1.f - pows[0], bc2 = 1.f - pows[1];
   const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,11 +41,11 @@ extern "C" int vargp_yogi_step(float* p, const float* g, float* m, float* v, int
   if (!p || !g || !m || !v || !pows || n < 0) return VARGP_ERR_ARG;
   if (n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  yogi_advance_kernel<<<1, 1, 0, s>>>(pows, b1, b2);
+  launch_k(yogi_advance_kernel, dim3(1), dim3(1), 0, s, pows, b1, b2);
   int rc = launch_status();
   if (rc) return rc;
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  yogi_step_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, pows);
+  launch_k(yogi_step_kernel, dim3((unsigned)blocks), dim3(256), 0, s, p, g, m, v, n, lr, b1, b2, eps, pows);
   return launch_status();
 }

@@ -32,6 +32,7 @@ namespace vargp {
 __global__ void __launch_bounds__(256)
 potrf_init_kernel(const float* __restrict__ A, int64_t a_ld, int64_t a_bs, float* __restrict__ W, int64_t w_ld,
                   int64_t w_bs, int n, float jitter) {
+  pdl_enter();
   const int64_t b = blockIdx.z;
   const int i = blockIdx.y;
   const int j = blockIdx.x * 256 + threadIdx.x;
@@ -47,6 +48,7 @@ potrf_init_kernel(const float* __restrict__ A, int64_t a_ld, int64_t a_bs, float
 // zero the strict upper triangle outside the nb x nb diagonal blocks (those are zero-filled by the block kernels)
 __global__ void __launch_bounds__(256)
 zero_upper_kernel(float* __restrict__ L, int64_t ld, int64_t bs, int n, int nb) {
+  pdl_enter();
   const int64_t b = blockIdx.z;
   const int i = blockIdx.y;
   const int j0 = (i / nb + 1) * nb;
@@ -108,7 +110,7 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     return vargp_trtri(L, l_ld, l_bs, W, w_ld, w_bs, n, batch, stream);
   }
 
-  potrf_init_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch), 256, 0, s>>>(
+  launch_k(potrf_init_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch)), dim3(256), 0, s, 
       A, a_ld, a_bs, W, w_ld, w_bs, (int)n, jitter);
   int rc = launch_status();
   if (rc) return rc;
@@ -199,7 +201,7 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     }
   }
   if (n > nb) {
-    zero_upper_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch), 256, 0, s>>>(L, l_ld, l_bs,
+    launch_k(zero_upper_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch)), dim3(256), 0, s, L, l_ld, l_bs,
                                                                                                     (int)n, nb);
     rc = launch_status();
     if (rc) return rc;

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1)
 potrf_inv_small_kernel(const float* Ain, int64_t a_ld, int64_t a_bs, float* Lout, int64_t l_ld, int64_t l_bs,
                        float* Wout, int64_t w_ld, int64_t w_bs, int n, float jitter, int32_t* __restrict__ info,
                        int info_base, int accumulate) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   float* Ls = sm;
   float* Ws = Ls + SMAX * SLD;
@@ -282,7 +283,7 @@ extern "C" int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  potrf_inv_small_kernel<<<(unsigned)batch, kSmallThreads, dyn, (cudaStream_t)stream>>>(
+  launch_k(potrf_inv_small_kernel, dim3((unsigned)batch), dim3(kSmallThreads), dyn, (cudaStream_t)stream, 
       A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, (int)n, jitter, info, (int)info_base, accumulate);
   return launch_status();
 }

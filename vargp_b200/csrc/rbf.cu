@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(kScaleWarps * 32)
 scale_rows_kernel(const float* __restrict__ src, int64_t R, int64_t D, int64_t src_rs,
                   const float* __restrict__ theta, int64_t theta_rs,
                   float* __restrict__ dst, float* __restrict__ norms) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_isig[];
   const int h = blockIdx.y;
   for (int64_t d = threadIdx.x; d < D; d += blockDim.x) s_isig[d] = expf(-theta[h * theta_rs + d]);
@@ -68,6 +69,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kPrepThreads)
 rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64_t C, int64_t Pa, int64_t Pb,
                     int rows_blk, float* __restrict__ rsum, float* __restrict__ csum, float* __restrict__ dsum) {
+  pdl_enter();
   __shared__ float s_red[kPrepRS][kPrepThreads / 32 + 1];
   const int64_t g = blockIdx.z;
   const int64_t h = g / C;
@@ -155,6 +157,7 @@ rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz
                       const float* __restrict__ r1, const float* __restrict__ r2, const float* __restrict__ dg,
                       const float* __restrict__ theta, int64_t theta_rs, int64_t H, int64_t R, int64_t D,
                       float* __restrict__ Zbar, float* __restrict__ theta_bar) {
+  pdl_enter();
   const int64_t d = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.y * kFinRows;
   const int rows = (int)min((int64_t)kFinRows, R - row0);
@@ -197,6 +200,7 @@ constexpr int kXsRows = 64;
 __global__ void __launch_bounds__(128)
 rbf_bwd_xside_theta_kernel(const float* __restrict__ xs, const float* __restrict__ csum, int64_t B, int64_t D,
                            float* __restrict__ theta_bar) {
+  pdl_enter();
   const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
   const int64_t h = blockIdx.z;
   const int64_t j0 = (int64_t)blockIdx.y * kXsRows;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(128)
 rbf_bwd_xside_x_kernel(const float* __restrict__ xs, const float* __restrict__ csum, const float* __restrict__ Gx,
                        const float* __restrict__ theta, int64_t theta_rs, int64_t H, int64_t C, int64_t B, int64_t D,
                        float* __restrict__ xbar) {
+  pdl_enter();
   const int64_t d = (int64_t)blockIdx.x * 128 + threadIdx.x;
   const int64_t j = blockIdx.y;
   if (d >= D) return;
@@ -238,7 +243,7 @@ extern "C" int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t 
   if (R == 0) return 0;
   if (D * sizeof(float) > 48 * 1024) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(R, kScaleWarps * kScaleRowsPerWarp), (unsigned)H);
-  scale_rows_kernel<<<grid, kScaleWarps * 32, D * sizeof(float), (cudaStream_t)stream>>>(
+  launch_k(scale_rows_kernel, dim3(grid), dim3(kScaleWarps * 32), D * sizeof(float), (cudaStream_t)stream, 
       src, R, D, src_rs, theta, theta_rs, dst, norms);
   return launch_status();
 }
@@ -265,8 +270,8 @@ extern "C" int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_
     if (e != cudaSuccess) return (int)e;
   }
   dim3 grid((unsigned)ctiles, (unsigned)chunks, (unsigned)G);
-  if (vec4) rbf_bwd_prep_kernel<4><<<grid, kPrepThreads, 0, s>>>(Kbar, K, C, Pa, Pb, (int)rows_blk, rsum, csum, dsum);
-  else rbf_bwd_prep_kernel<1><<<grid, kPrepThreads, 0, s>>>(Kbar, K, C, Pa, Pb, (int)rows_blk, rsum, csum, dsum);
+  if (vec4) launch_k((rbf_bwd_prep_kernel<4>), dim3(grid), dim3(kPrepThreads), 0, s, Kbar, K, C, Pa, Pb, (int)rows_blk, rsum, csum, dsum);
+  else launch_k((rbf_bwd_prep_kernel<1>), dim3(grid), dim3(kPrepThreads), 0, s, Kbar, K, C, Pa, Pb, (int)rows_blk, rsum, csum, dsum);
   return launch_status();
 }
 
@@ -278,7 +283,7 @@ extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const flo
   const int64_t R = C * P;
   if (ceil_div(R, kFinRows) > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows));
-  rbf_bwd_finish_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs, H, R,
+  launch_k(rbf_bwd_finish_kernel, dim3(grid), dim3(kFinThreads), 0, (cudaStream_t)stream, zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs, H, R,
                                                                          D, Zbar, theta_bar);
   return launch_status();
 }
@@ -291,11 +296,11 @@ extern "C" int vargp_rbf_bwd_xside(const float* xs, const float* csum, const flo
   if (ceil_div(B, kXsRows) > 65535 || H > 65535 || B > 65535 * 64) return VARGP_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(B, kXsRows), (unsigned)H);
-  rbf_bwd_xside_theta_kernel<<<grid, 128, 0, s>>>(xs, csum, B, D, theta_bar);
+  launch_k(rbf_bwd_xside_theta_kernel, dim3(grid), dim3(128), 0, s, xs, csum, B, D, theta_bar);
   int rc = launch_status();
   if (rc || !xbar) return rc;
   if (B > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid2((unsigned)ceil_div(D, 128), (unsigned)B);
-  rbf_bwd_xside_x_kernel<<<grid2, 128, 0, s>>>(xs, csum, Gx, theta, theta_rs, H, C, B, D, xbar);
+  launch_k(rbf_bwd_xside_x_kernel, dim3(grid2), dim3(128), 0, s, xs, csum, Gx, theta, theta_rs, H, C, B, D, xbar);
   return launch_status();
 }
