@@ -204,7 +204,7 @@ def run_gpu(args):
   use_graph = (not args.no_graph) and wl != 'scaled'
   from vargp_b200.train import ElboStepper
   stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
-                        use_graph=use_graph)
+                        use_graph=use_graph, shard_factor=False if args.no_shard_factor else None)
   # minibatch pool larger than the 126 MB L2, rotated every step
   n_pool = max(4, math.ceil(260e6 / (B * D * 4)))
   xs, ys = synth_batches(n_pool, B, D, C, task, dev, seed=rank)
@@ -328,7 +328,7 @@ def run_gpu(args):
     'config': {'workload': f'{wl} shape, task t={task}: C={C}, D={D}, M={cfg["M"]}/task, P={(task + 1) * cfg["M"]}, '
                            f'B={B}/rank, H={H}, F={F}, beta={cfg["beta"]}, Yogi',
                'l2': f'inputs rotate over a {n_pool * B * D * 4 / 1e6:.0f} MB minibatch pool (> 126 MB L2)',
-               'parallelism': f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL replicated, 1 NCCL all-reduce/step',
+               'parallelism': (f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL ' + ('sharded over (h,c) pairs (all-gather W,N,nu; reduce-scatter Wbar,G,nubar)' if stepper.shard is not None else 'replicated') + ', 1 NCCL gradient all-reduce/step'),
                'cuda_graph': bool(use_graph)},
     'e2e': {'value': round(e2e_v if wl != 'scaled' else K / (ms_e2e * 1e-3), 3), 'unit': 'steps/s',
             'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 12, 'ms_per_step': round(ms_e2e / K, 4)},
@@ -385,6 +385,7 @@ def main():
   ap.add_argument('--batch', type=int, default=None, help='override the (global) minibatch size of the workload')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
+  ap.add_argument('--no-shard-factor', action='store_true', help='N > 1: keep the O(P^3) factor stage replicated on every rank')
   ap.add_argument('--verbose', action='store_true', help='progress lines on stderr')
   ap.add_argument('--detail', action='store_true', help='add per-call-site kernel times to the JSON line')
   args = ap.parse_args()

@@ -35,9 +35,10 @@ class GradBucket:
         p.grad.copy_(v)
 
 
-def shard_coef(beta, n_data, global_batch, world_size):
-  """Coefficients of (kl_hypers, kl_u, nll_local) in the per-rank loss."""
-  return (beta / world_size, 1.0 / world_size, n_data / global_batch)
+def shard_coef(beta, n_data, global_batch, world_size, factor_sharded=False):
+  """Coefficients of (kl_hypers, kl_u, nll_local) in the per-rank loss.  With the factor stage sharded
+  (elbo.FactorShard) every rank holds only its share of kl_u, so that term enters with weight 1."""
+  return (beta / world_size, 1.0 if factor_sharded else 1.0 / world_size, n_data / global_batch)
 
 
 def shard_loss(kl_hypers, kl_u, nll_local, beta, n_data, global_batch, world_size, coef=None):

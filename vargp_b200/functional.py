@@ -19,11 +19,11 @@ class MarginalFn(torch.autograd.Function):
   """
 
   @staticmethod
-  def forward(ctx, theta, Zcat, x, m_all, Lu_all, M, want_kl):
+  def forward(ctx, theta, Zcat, x, m_all, Lu_all, M, want_kl, shard=None):
     c = elbo._Ctx()
     f_mean, f_var, kl, info, L = elbo.marginal_forward(
       theta.detach().contiguous(), Zcat.detach().contiguous(), x.detach().contiguous(),
-      m_all.detach().contiguous(), Lu_all.detach().contiguous(), M, want_kl, c)
+      m_all.detach().contiguous(), Lu_all.detach().contiguous(), M, want_kl, c, shard=shard)
     ctx.c = c
     ctx.need_x = x.requires_grad
     ctx.want_kl = want_kl
@@ -41,7 +41,7 @@ class MarginalFn(torch.autograd.Function):
       g_kl = g_kl.detach().reshape(1).contiguous()
     th_bar, Z_bar, x_bar, m_bar, Lu_bar = elbo.marginal_backward(ctx.c, g_mean, g_var, g_kl, need_x_grad=ctx.need_x)
     ctx.c = None
-    return th_bar, Z_bar, x_bar, m_bar, Lu_bar, None, None
+    return th_bar, Z_bar, x_bar, m_bar, Lu_bar, None, None, None
 
 
 class TrilUnpackFn(torch.autograd.Function):

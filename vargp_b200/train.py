@@ -17,24 +17,40 @@ from .optim import FlatYogi
 
 
 class ElboStepper:
-  def __init__(self, gp, n_data, batch_size, beta=1.0, lr=1e-2, world_size=1, use_graph=True, optimizer=None):
+  def __init__(self, gp, n_data, batch_size, beta=1.0, lr=1e-2, world_size=1, use_graph=True, optimizer=None,
+               shard_factor=None):
+    """shard_factor: also shard the replicated O(P^3) factor stage over the ranks (elbo.FactorShard); default: on
+    when world_size > 1 and the task has at least 512 inducing points per class (below that the three extra
+    collectives cost more than the replicated work)."""
     self.gp, self.n_data, self.beta, self.world = gp, n_data, beta, world_size
     self.global_batch = batch_size * world_size
     self.opt = optimizer or FlatYogi(gp.parameters(), lr=lr)
+    P = (gp.n_prev + 1) * gp.M
+    if shard_factor is None:
+      shard_factor = world_size > 1 and P >= 512
+    self.shard = None
+    if shard_factor and world_size > 1 and gp.var_mean_mask == 1.0:
+      from .elbo import FactorShard
+      self.shard = FactorShard()
+      use_graph = False                    # collectives inside forward / backward: launch eagerly
     self.use_graph = use_graph
     self.graph = None
     dev = next(gp.parameters()).device
     D = gp.z.size(-1) if not hasattr(gp.kernel, 'phi') else gp.kernel.phi[0].in_features
     self.x = torch.empty(batch_size, D, device=dev)
     self.y = torch.empty(batch_size, dtype=torch.int64, device=dev)
-    self.coef = torch.tensor(shard_coef(beta, n_data, self.global_batch, world_size), device=dev)
+    self.coef = torch.tensor(shard_coef(beta, n_data, self.global_batch, world_size, self.shard is not None), device=dev)
     self.terms = None
     self.launches_per_step = None
     gp.sync_errors = False
 
   def _grad_body(self):
     self.opt.zero_grad()
-    kl_h, kl_u, nll = self.gp.loss(self.x, self.y)
+    self.gp.factor_shard = self.shard
+    try:
+      kl_h, kl_u, nll = self.gp.loss(self.x, self.y)
+    finally:
+      self.gp.factor_shard = None
     loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
     loss.backward()
     return kl_h.detach(), kl_u.detach(), nll.detach()

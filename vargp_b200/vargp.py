@@ -54,6 +54,7 @@ class VARGP(nn.Module):
     self.u_mean = nn.Parameter(torch.Tensor(out_size, self.M, 1).normal_(0., .5))
     self.u_tril_vec = nn.Parameter(mat2trilvec(torch.eye(self.M).unsqueeze(0).expand(out_size, -1, -1)))
 
+    self.factor_shard = None      # elbo.FactorShard while a data-parallel training step shards the O(P^3) work
     self.sync_errors = True       # raise LinAlgError from loss()/predict() like torch.cholesky would
     self._last_info = None
 
@@ -93,7 +94,7 @@ class VARGP(nn.Module):
   def _marginal(self, x, theta, want_kl):
     Zf, m_all, Lu_all = self._assemble()
     xf = self.kernel.features(x)
-    f_mean, f_var, kl, info, L = MarginalFn.apply(theta, Zf, xf, m_all, Lu_all, self.M, want_kl)
+    f_mean, f_var, kl, info, L = MarginalFn.apply(theta, Zf, xf, m_all, Lu_all, self.M, want_kl, self.factor_shard)
     self._last_info = info
     if self.sync_errors:
       self.check_errors()
