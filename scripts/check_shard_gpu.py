@@ -12,8 +12,15 @@ from vargp_b200.dist import shard_coef
 from vargp_b200.elbo import FactorShard
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
-torch.cuda.set_device(local)
-dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+# VARGP_CHECK_BACKEND=gloo: all ranks share cuda:0 and the collectives go through gloo (host staged) -- checks the
+# kernels on the sharded (h, c) sub-rectangles on a single-GPU box; the default is one GPU per rank over NCCL.
+backend = os.environ.get('VARGP_CHECK_BACKEND', 'nccl')
+if backend == 'nccl':
+  torch.cuda.set_device(local)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+else:
+  torch.cuda.set_device(0)
+  dist.init_process_group(backend)
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 640
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 params, prev, x, y, noise = make_case(C=10, D=784, M=P, t=0, B=B * world, sigma=10., seed=5)
@@ -40,7 +47,7 @@ for mode in ('replicated', 'sharded'):
   res[mode] = (flat, klu, dt)
 if rank == 0:
   f0, k0, t0 = res['replicated']; f1, k1, t1 = res['sharded']
-  print(json.dumps(dict(world=world, P=P, B_per_rank=B, grad_relerr=((f0 - f1).norm() / f0.norm()).item(),
+  print(json.dumps(dict(backend=backend, world=world, P=P, B_per_rank=B, grad_relerr=((f0 - f1).norm() / f0.norm()).item(),
                         kl_u_relerr=abs((k0 - k1).item()) / abs(k0.item()), ms_replicated=round(1e3 * t0, 2),
                         ms_sharded=round(1e3 * t1, 2))))
 dist.destroy_process_group()
