@@ -302,3 +302,99 @@ def predict(params, prev, x, noise, n_v, map_est=False):
 
 # seeded synthetic cases live with the product's data utilities
 from vargp_b200.synthetic import make_case  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------------------------
+# var_gp/vargp_retrain.py  (ablation: every previous task's variational parameters are re-trained)
+# ----------------------------------------------------------------------------------------------
+LOG_2PI = math.log(2. * math.pi)
+
+
+def mvn_log_prob_tril(value, mu, L):
+  """torch.distributions.MultivariateNormal(mu, scale_tril=L).log_prob(value) (torch 2.11):
+  -(n log 2pi + |L^-1 (value - mu)|^2) / 2 - sum log diag L."""
+  diff = (value - mu).unsqueeze(-1)
+  maha = _lsolve(L, diff).pow(2).sum((-2, -1))
+  return -0.5 * (mu.size(-1) * LOG_2PI + maha) - L.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+
+
+def retrain_compute_q(theta, chain, z, u_mean, u_tril_vec):
+  """var_gp/vargp_retrain.py:40-95: the autoregressive joint over `chain` (tasks < t, dicts with the PACKED
+  u_tril_vec) followed by the current task.  Returns mu_lt, S_lt, mu_leq, S_leq, z_lt, z_leq."""
+  H = theta.size(0)
+  z_lt = chain[0]['z']
+  mu_lt = chain[0]['u_mean'].unsqueeze(0).expand(H, -1, -1, -1)
+  S_lt = llt(vec2tril(chain[0]['u_tril_vec'])).unsqueeze(0).expand(H, -1, -1, -1)
+  for p in chain[1:]:
+    Kzx = rbf_compute(theta, z_lt, p['z'])
+    Kzz = rbf_compute(theta, z_lt)
+    V = llt(vec2tril(p['u_tril_vec'])).unsqueeze(0).expand(H, -1, -1, -1)
+    b = p['u_mean'].unsqueeze(0).expand(H, -1, -1, -1)
+    mu_lt, S_lt = linear_joint(mu_lt, S_lt, Kzx, Kzz, V, b)
+    z_lt = torch.cat([z_lt, p['z']], dim=-2)
+  Kzx = rbf_compute(theta, z_lt, z)
+  Kzz = rbf_compute(theta, z_lt)
+  V = llt(vec2tril(u_tril_vec)).unsqueeze(0).expand(H, -1, -1, -1)
+  b = u_mean.unsqueeze(0).expand(H, -1, -1, -1)
+  mu_leq, S_leq = linear_joint(mu_lt, S_lt, Kzx, Kzz, V, b)
+  return mu_lt, S_lt, mu_leq, S_leq, z_lt, torch.cat([z_lt, z], dim=-2)
+
+
+def retrain_elbo_terms(params, retrain, prev, x, y, noise, n_v):
+  """var_gp/vargp_retrain.py:126-237 -> (kl_hypers, kl_u, nll).
+
+  params:  current task (z, u_mean, u_tril_vec, log_mean, log_logvar, prior_*)
+  retrain: trainable copies of the previous tasks' (z, u_mean, u_tril_vec)   [self.retrain_params]
+  prev:    the frozen previous posteriors                                    [self.prev_params]
+  noise:   eps_theta (H, D+1); if prev: eps_q (n_v, H, C, P), eps_p (n_v, n_v, H, C, Q); eps_f (H, F, C, B)
+           -- the reference's draw order: hypers, q_leq_t.sample, p_lt_tilde.sample, likelihood.
+  """
+  theta = sample_hypers(params['log_mean'], params['log_logvar'], noise['eps_theta'])
+  z, u_mean, u_tril_vec = params['z'], params['u_mean'], params['u_tril_vec']
+  M = z.size(-2)
+  kl_h = kl_hypers(params['log_mean'], params['log_logvar'], params['prior_log_mean'], params['prior_log_logvar'])
+  if not prev:
+    cpf = dict()
+    L_u = vec2tril(u_tril_vec, M)
+    f_mean, f_var = compute_pf_diag(theta, x, u_mean, llt(L_u), z, cache=cpf)
+    nll = softmax_nll(f_mean, f_var, y, noise['eps_f'])
+    mu_t = u_mean.squeeze(-1).unsqueeze(0).unsqueeze(0)
+    kl = mvn_kl_tril(mu_t, L_u.unsqueeze(0).unsqueeze(0), torch.zeros_like(mu_t), cpf['Lz'].unsqueeze(0))
+    return kl_h, kl.sum(-1).mean(0).mean(0), nll
+
+  _, _, mu_leq, S_leq, _, z_leq = retrain_compute_q(theta, retrain, z, u_mean, u_tril_vec)
+  f_mean, f_var = compute_pf_diag(theta, x, mu_leq, S_leq, z_leq)
+  # p(u_<=t | theta), q(u~_<t | theta) from the FROZEN posteriors, p(u~_<t | theta)       [:147-157]
+  prior_S_leq = rbf_compute(theta, z_leq)
+  mu_tl, S_tl, _, _, z_tl, _ = retrain_compute_q(theta, prev, z, u_mean, u_tril_vec)
+  prior_S_tl = rbf_compute(theta, z_tl)
+  # u_<=t ~ q (non-reparametrised .sample), u~_<t ~ p(u~_<t | u_<=t, theta)                [:159-169]
+  L_q = chol_jitter(S_leq)
+  with torch.no_grad():
+    u_leq = (mu_leq.squeeze(-1).unsqueeze(0) + (L_q.unsqueeze(0) @ noise['eps_q'].unsqueeze(-1)).squeeze(-1)).unsqueeze(-1)
+    Kzz = rbf_compute(theta, z_leq).unsqueeze(0).expand(n_v, -1, -1, -1, -1)
+    Kzx = rbf_compute(theta, z_leq, z_tl).unsqueeze(0).expand(n_v, -1, -1, -1, -1)
+    Kxx = rbf_compute(theta, z_tl).unsqueeze(0).expand(n_v, -1, -1, -1, -1)
+    p_mu, p_S = gp_cond(u_leq, Kzz, Kzx, Kxx)
+    L_p = chol_jitter(p_S)
+    u_tl = p_mu.squeeze(-1).unsqueeze(0) + (L_p.unsqueeze(0) @ noise['eps_p'].unsqueeze(-1)).squeeze(-1)
+  nll = softmax_nll(f_mean, f_var, y, noise['eps_f'])
+  # loss                                                                                   [:197-222]
+  kl = mvn_kl_tril(mu_leq.squeeze(-1), L_q, torch.zeros_like(mu_leq.squeeze(-1)), chol_jitter(prior_S_leq))
+  kl_u = kl.sum(-1).mean(0)
+  mu_tl = mu_tl.squeeze(-1)
+  ratio = mvn_log_prob_tril(u_tl, torch.zeros_like(mu_tl), chol_jitter(prior_S_tl)) \
+      - mvn_log_prob_tril(u_tl, mu_tl, chol_jitter(S_tl))
+  return kl_h, kl_u + ratio.sum(-1).mean(-1).mean(-1).mean(-1), nll
+
+
+def retrain_predict(params, retrain, x, noise):
+  """var_gp/vargp_retrain.py:239-241 -> probs (B, C)."""
+  theta = sample_hypers(params['log_mean'], params['log_logvar'], noise['eps_theta'])
+  z, u_mean, u_tril_vec = params['z'], params['u_mean'], params['u_tril_vec']
+  if retrain:
+    _, _, mu_leq, S_leq, _, z_leq = retrain_compute_q(theta, retrain, z, u_mean, u_tril_vec)
+    f_mean, f_var = compute_pf_diag(theta, x, mu_leq, S_leq, z_leq)
+  else:
+    f_mean, f_var = compute_pf_diag(theta, x, u_mean, llt(vec2tril(u_tril_vec, z.size(-2))), z)
+  return softmax_predict(f_mean, f_var, noise['eps_f'])

@@ -40,6 +40,14 @@ CASES = {
 }
 MODEL_FLAGS = ('ep_var_mean', 'map_est')
 
+# VARGPRetrain ablation (var_gp/vargp_retrain.py): name -> make_retrain_case kwargs; fixtures retrain_*.pt
+RETRAIN_CASES = {
+  'retrain_toy_t0':   dict(C=4, D=2, M=20, t=0, B=100, sigma=0.25, seed=41),
+  'retrain_toy_t1':   dict(C=4, D=2, M=20, t=1, B=100, sigma=0.25, seed=42),
+  'retrain_mnist_t1': dict(C=10, D=784, M=12, t=1, B=48, sigma=10., seed=43),
+  'retrain_odd_t2':   dict(C=3, D=37, M=7, t=2, B=33, sigma=3., seed=44, H=2, F=5),
+}
+
 
 def load_reference():
   sys.path.insert(0, REF)
@@ -158,8 +166,84 @@ def run_reference(refmods, kw, dtype):
     torch.set_default_dtype(old)
 
 
+def _close(a, b, name, dtype, tol32=5e-5):
+  tol = tol32 if dtype == torch.float32 else 1e-10
+  err = (a.double() - b.double()).abs().max().item()
+  ref = b.double().abs().max().item()
+  assert err <= tol * max(ref, 1e-30) + (1e-7 if dtype == torch.float32 else 1e-14), (name, err, ref)
+
+
+def run_reference_retrain(kw, dtype):
+  """The live VARGPRetrain (var_gp/vargp_retrain.py) on a seeded case; its four draws pinned in the reference's
+  order (hypers, q_leq_t.sample, p_lt_tilde.sample, likelihood)."""
+  from oracle import vargp_oracle as orc
+  from vargp_b200.synthetic import make_retrain_case
+  from var_gp.vargp_retrain import VARGPRetrain
+  from var_gp.kernels import RBFKernel
+  from var_gp.likelihoods import MulticlassSoftmax
+  H, F = kw.get('H', 3), kw.get('F', 10)
+  old = torch.get_default_dtype()
+  torch.set_default_dtype(dtype)
+  try:
+    params, retrain, prev, x, y, noise = make_retrain_case(dtype=dtype, **kw)
+    D = params['z'].size(-1)
+    kern = RBFKernel(D, prior_log_mean=params['prior_log_mean'].clone(), prior_log_logvar=params['prior_log_logvar'].clone())
+    # the constructor wraps the tensors it is given into the trainable retrain_params (sharing storage); the frozen
+    # posteriors self.prev_params are then pointed at separate tensors so that the two sets differ
+    gp = VARGPRetrain(params['z'].clone(), kern, MulticlassSoftmax(n_f=F), n_var_samples=H,
+                      prev_params=[{k: v.clone() for k, v in p.items()} for p in retrain] or None)
+    if prev:
+      gp.prev_params = [{k: v.clone() for k, v in p.items()} for p in prev]
+    with torch.no_grad():
+      gp.u_mean.copy_(params['u_mean'])
+      gp.u_tril_vec.copy_(params['u_tril_vec'])
+      gp.kernel.log_mean.copy_(params['log_mean'])
+      gp.kernel.log_logvar.copy_(params['log_logvar'])
+    draws = [noise['eps_theta']] + ([noise['eps_q'], noise['eps_p']] if prev else []) + [noise['eps_f']]
+    with pinned_noise(draws):
+      kl_h, kl_u, nll = gp.loss(x, y)
+    Ntot, beta = 10 * x.size(0), 1.7
+    total = beta * kl_h + kl_u + (Ntot / x.size(0)) * nll
+    gp.zero_grad()
+    total.backward()
+    grads = dict(z=gp.z.grad, u_mean=gp.u_mean.grad, u_tril_vec=gp.u_tril_vec.grad,
+                 log_mean=gp.kernel.log_mean.grad, log_logvar=gp.kernel.log_logvar.grad)
+    for s in range(len(prev)):
+      for k in ('z', 'u_mean', 'u_tril_vec'):
+        grads[f'retrain.{s}.{k}'] = gp.retrain_params[s][k].grad
+    with torch.no_grad(), pinned_noise([noise['eps_theta'], noise['eps_f']]):
+      probs = gp.predict(x)
+    out = dict(kl_hypers=kl_h.detach(), kl_u=kl_u.detach(), nll=nll.detach(), total=total.detach(), probs=probs,
+               beta=beta, Ntot=Ntot, grads={k: v.detach().clone() for k, v in grads.items()})
+
+    # --- the oracle restatement must reproduce the reference ---
+    leaf = lambda d: {k: v.clone().requires_grad_(True) if v.is_floating_point() and not k.startswith('prior') else v
+                      for k, v in d.items()}
+    op, ort = leaf(params), [leaf(p) for p in retrain]
+    okl_h, okl_u, onll = orc.retrain_elbo_terms(op, ort, prev, x, y, noise, n_v=H)
+    (beta * okl_h + okl_u + (Ntot / x.size(0)) * onll).backward()
+    _close(okl_h, kl_h, 'kl_h', dtype); _close(okl_u, kl_u, 'kl_u', dtype, 2e-4); _close(onll, nll, 'nll', dtype)
+    for k, g in grads.items():
+      src = ort[int(k.split('.')[1])][k.split('.')[2]] if k.startswith('retrain') else op[k]
+      _close(src.grad, g, 'grad ' + k, dtype, 2e-4)
+    _close(orc.retrain_predict(params, retrain, x, noise), probs, 'probs', dtype)
+    return out
+  finally:
+    torch.set_default_dtype(old)
+
+
 def main():
   refmods = load_reference()
+  for name, kw in RETRAIN_CASES.items():
+    rec = dict(case=kw, torch=torch.__version__)
+    for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+      rec[tag] = run_reference_retrain(kw, dtype)
+    path = os.path.join(HERE, name + '.pt')
+    torch.save(rec, path)
+    print(f'{name:24s} kl_u={rec["f64"]["kl_u"].item():.6f} nll={rec["f64"]["nll"].item():.6f} '
+          f'-> {os.path.getsize(path) / 1024:.0f} KiB')
+  if os.environ.get('VARGP_GOLDEN_ONLY') == 'retrain':
+    return
   for name, kw in CASES.items():
     rec = dict(case=kw, torch=torch.__version__)
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):

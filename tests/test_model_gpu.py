@@ -185,6 +185,12 @@ def test_dkl_fused_path_agrees_with_composed(cuda_ops):
   assert util.relerr(kl_u2, kl_u) < 1e-4 and util.relerr(nll2, nll) < 1e-4 and util.relerr(kl_h2, kl_h) < 1e-5
   assert any(k.startswith('kernel.phi') for k in g_f)
   for k in g_c:
+    if k == 'kernel.phi.4.bias':
+      # the RBF kernel only sees feature differences, so the bias of the last layer has an exactly zero gradient
+      # (2e-9 in fp64); in fp32 both paths return the rounding noise of a sum of O(1e5) cancelling terms
+      for gk in (g_f[k], g_c[k]):
+        assert gk.norm() < 1e-4 * g_f['kernel.phi.4.weight'].norm(), k
+      continue
     assert g_c[k].abs().max() > 0, k
     # two fp32 evaluation orders of an ill-scaled random-MLP feature map: the hyper-variance gradient (a sum of large
     # cancelling terms) is the most sensitive one (7.8e-4 measured), everything else agrees to < 5e-4

@@ -61,3 +61,40 @@ def test_state_dict_keys_match_reference(emu_ops):
   gp = util.build_model(params, prev, n_v, F, flags, 'cpu', torch.float32)
   assert list(gp.state_dict().keys()) == ['z', 'u_mean', 'u_tril_vec', 'kernel.log_mean', 'kernel.log_logvar',
                                           'kernel.prior_log_mean', 'kernel.prior_log_logvar']
+
+
+def test_dkl_fused_schedule_agrees_with_composed_fp64(emu_ops):
+  """DeepRBFKernel (var_gp/kernels.py:80-96): through the `features` hook the fused schedule (with the
+  x-side RBF adjoint that carries gradients back into phi) and the reference-order composed path are the same function
+  of every parameter, incl. the MLP weights: fp64 agreement to 1e-10.  The bias of the last MLP layer has an exactly
+  zero gradient (the RBF kernel is shift invariant)."""
+  from vargp_b200.vargp import VARGP
+  from vargp_b200.kernels import DeepRBFKernel
+  from vargp_b200.likelihoods import MulticlassSoftmax
+  from vargp_b200.composed import loss_composed
+  torch.manual_seed(0)
+  C, Din, M, B, Fd = 4, 20, 9, 48, 16
+  g = torch.Generator().manual_seed(5)
+  prev = [dict(z=torch.rand(C, M, Din, generator=g), u_mean=0.5 * torch.randn(C, M, 1, generator=g),
+               u_tril_vec=0.1 * torch.randn(C, M * (M + 1) // 2, generator=g))]
+  gp = VARGP(torch.rand(C, M, Din, generator=g), DeepRBFKernel(Din, feature_size=Fd), MulticlassSoftmax(n_f=5),
+             n_var_samples=2, prev_params=prev)
+  with torch.no_grad():
+    gp.kernel.log_mean[:Fd] = 0.3
+  gp = gp.double()
+  x, y = torch.rand(B, Din, generator=g).double(), torch.randint(0, C, (B,), generator=g)
+  nz = dict(eps_theta=torch.randn(2, Fd + 1, generator=g).double(), eps_f=torch.randn(2, 5, C, B, generator=g).double(),
+            eps_u=torch.randn(2, 2, C, M, generator=g).double())
+  grads = lambda: {n: p.grad.detach().clone() for n, p in gp.named_parameters()}
+  kl_h, kl_u, nll = loss_composed(gp, x, y, nz)
+  gp.zero_grad(); (kl_h + kl_u + 7. * nll).backward()
+  g_c = grads()
+  kl_h2, kl_u2, nll2 = gp.loss(x, y, noise=nz)
+  gp.zero_grad(); (kl_h2 + kl_u2 + 7. * nll2).backward()
+  g_f = grads()
+  assert util.relerr(kl_u2, kl_u) < 1e-10 and util.relerr(nll2, nll) < 1e-10
+  for k in g_c:
+    if k == 'kernel.phi.4.bias':
+      assert g_f[k].norm() < 1e-10 * g_f['kernel.phi.4.weight'].norm()
+    else:
+      assert util.relerr(g_f[k], g_c[k]) < 1e-10, k

@@ -11,7 +11,13 @@ GRAD_KEYS = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
 
 
 def golden_names():
-  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt'))
+  """VARGP fixtures (make_golden.CASES)."""
+  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith('retrain_'))
+
+
+def retrain_names():
+  """VARGPRetrain fixtures (make_golden.RETRAIN_CASES)."""
+  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and f.startswith('retrain_'))
 
 
 def load_golden(name):
@@ -73,3 +79,37 @@ def run_model(gp, x, y, noise, beta, Ntot):
   gp.zero_grad()
   total.backward()
   return dict(kl_hypers=kl_h, kl_u=kl_u, nll=nll, total=total), model_grads(gp)
+
+
+def build_retrain_model(params, retrain, prev, n_v, F, device, dtype):
+  """vargp_b200.VARGPRetrain carrying a make_retrain_case: trainable copies = `retrain`, frozen posteriors = `prev`."""
+  from vargp_b200.vargp_retrain import VARGPRetrain
+  from vargp_b200.kernels import RBFKernel
+  from vargp_b200.likelihoods import MulticlassSoftmax
+  D = params['z'].size(-1)
+  kern = RBFKernel(D, prior_log_mean=params['prior_log_mean'].clone(), prior_log_logvar=params['prior_log_logvar'].clone())
+  gp = VARGPRetrain(params['z'].clone(), kern, MulticlassSoftmax(n_f=F), n_var_samples=n_v,
+                    prev_params=[{k: v.clone() for k, v in p.items()} for p in prev]).to(dtype)
+  with torch.no_grad():
+    gp.u_mean.copy_(params['u_mean'])
+    gp.u_tril_vec.copy_(params['u_tril_vec'])
+    gp.kernel.log_mean.copy_(params['log_mean'])
+    gp.kernel.log_logvar.copy_(params['log_logvar'])
+    for s, p in enumerate(retrain):
+      for k, v in p.items():
+        gp.retrain_params[s][k].copy_(v)
+  return gp.to(device)
+
+
+def run_retrain_model(gp, x, y, noise, beta, Ntot):
+  dev = gp.z.device
+  nz = {k: v.to(dev) for k, v in noise.items()}
+  kl_h, kl_u, nll = gp.loss(x.to(dev), y.to(dev), noise=nz)
+  total = beta * kl_h + kl_u + (Ntot / x.size(0)) * nll
+  gp.zero_grad()
+  total.backward()
+  grads = model_grads(gp)
+  for s in range(gp.n_prev):
+    for k in ('z', 'u_mean', 'u_tril_vec'):
+      grads[f'retrain.{s}.{k}'] = gp.retrain_params[s][k].grad
+  return dict(kl_hypers=kl_h, kl_u=kl_u, nll=nll, total=total), grads

@@ -34,3 +34,18 @@ def make_case(C, D, M, t, B, H=3, F=10, seed=0, sigma=10., dtype=torch.float32, 
   if t > 0 and with_eps_u:
     noise['eps_u'] = Nrm(n_v, H, C, t * M).to(dtype)
   return params, prev, x, y, noise
+
+
+def make_retrain_case(C, D, M, t, B, H=3, F=10, seed=0, sigma=10., dtype=torch.float32, sparse=False):
+  """`make_case` plus what the VARGPRetrain ablation needs (var_gp/vargp_retrain.py): trainable copies of the
+  previous tasks' parameters that have moved away from the frozen posteriors, and the two extra draws of its loss
+  (eps_q for u_<=t ~ q, eps_p for u~_<t ~ p(. | u_<=t)).  Returns (params, retrain, prev, x, y, noise)."""
+  params, prev, x, y, noise = make_case(C, D, M, t, B, H=H, F=F, seed=seed, sigma=sigma, dtype=dtype,
+                                        with_eps_u=False, sparse=sparse)
+  g = torch.Generator().manual_seed(seed + 1000)
+  Nrm = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+  retrain = [{k: (v.double() + 0.05 * Nrm(*v.shape)).to(dtype) for k, v in p.items()} for p in prev]
+  if t > 0:
+    noise['eps_q'] = Nrm(H, H, C, (t + 1) * M).to(dtype)
+    noise['eps_p'] = Nrm(H, H, H, C, t * M).to(dtype)
+  return params, retrain, prev, x, y, noise
