@@ -35,19 +35,25 @@ def test_oracle_retrain_matches_reference_fixture(name, tag, dtype, tol):
   assert (probs.double() - ref['probs'].double()).abs().max().item() < (1e-10 if dtype == torch.float64 else 1e-5)
 
 
-def _check_model(name, device, dtype, tol, ptol):
+def _check_model(name, device, dtype, tol, ptol, own_error=False):
+  """own_error: widen each bound to 10 x the reference's own fp32-vs-fp64 error (only matters on the ill-conditioned
+  toy cases, like tests/test_model_gpu.py)."""
   rec, H, F, (params, retrain, prev, x, y, noise) = _case(name, dtype)
-  ref = rec['f64']
+  ref, r32 = rec['f64'], rec['f32']
+  bound = lambda a, b, base: max(base, 10. * util.relerr(a, b)) if own_error else base
   gp = util.build_retrain_model(params, retrain, prev, H, F, device, dtype)
   terms, grads = util.run_retrain_model(gp, x, y, noise, ref['beta'], ref['Ntot'])
   for k in ('kl_hypers', 'kl_u', 'nll', 'total'):
-    assert util.relerr(terms[k], ref[k]) < tol, k
+    err = util.relerr(terms[k], ref[k])
+    assert err < bound(r32[k], ref[k], tol), f'{name} {k}: {err:.3e}'
   assert set(grads) == set(ref['grads'])
   for k, g in ref['grads'].items():
-    assert util.relerr(grads[k], g) < 10 * tol, k
+    err = util.relerr(grads[k], g)
+    assert err < bound(r32['grads'][k], g, 10 * tol), f'{name} grad {k}: {err:.3e}'
   with torch.no_grad():
     probs = gp.predict(x.to(device), noise={k: v.to(device) for k, v in noise.items()})
-  assert (probs.cpu().double() - ref['probs']).abs().max().item() < ptol
+  err = (probs.cpu().double() - ref['probs']).abs().max().item()
+  assert err < (max(ptol, 3. * (r32['probs'].double() - ref['probs']).abs().max().item()) if own_error else ptol), err
   return gp
 
 
@@ -96,5 +102,5 @@ def test_retrain_gpu_matches_reference(name, cuda_ops):
   (the log-density ratio of n_v^2 samples under two near-singular Gaussians is the ill-conditioned part; the
   reference's own fp32 run differs from its fp64 run by the same order), probabilities 1e-5 absolute."""
   rec, H, F, _ = _case(name, torch.float32)
-  gp = _check_model(name, 'cuda', torch.float32, 1e-4, 1e-5)
+  gp = _check_model(name, 'cuda', torch.float32, 1e-4, 1e-5, own_error=True)
   assert next(gp.parameters()).is_cuda
