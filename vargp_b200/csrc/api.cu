@@ -6,6 +6,7 @@
 namespace vargp {
 int64_t g_launches = 0;
 bool g_pdl = true;
+bool g_prio_attr = false;
 int g_device = -1;
 }  // namespace vargp
 
@@ -39,5 +40,7 @@ extern "C" int vargp_init(int device) {
   g_device = device;
   const char* pdl = getenv("VARGP_PDL");
   if (pdl) g_pdl = atoi(pdl) != 0;
+  const char* pa = getenv("VARGP_PRIO_ATTR");
+  if (pa) g_prio_attr = atoi(pa) != 0;
   return vargp_tc_init();
 }

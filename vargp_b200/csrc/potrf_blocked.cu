@@ -29,20 +29,26 @@ extern "C" int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, 
 
 namespace vargp {
 
+constexpr int kInitRows = 8;       // rows per CTA of the two passes below (one row per CTA was launch-bound)
+
 __global__ void __launch_bounds__(256)
 potrf_init_kernel(const float* __restrict__ A, int64_t a_ld, int64_t a_bs, float* __restrict__ W, int64_t w_ld,
                   int64_t w_bs, int n, float jitter) {
   pdl_enter();
   const int64_t b = blockIdx.z;
-  const int i = blockIdx.y;
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= n) return;
-  float v = 0.f;
-  if (j <= i) {
-    v = A[b * a_bs + (int64_t)i * a_ld + j];
-    if (j == i) v += jitter;
+  const int i0 = blockIdx.y * kInitRows;
+  float v[kInitRows];
+#pragma unroll
+  for (int r = 0; r < kInitRows; ++r) {
+    const int i = i0 + r;
+    v[r] = (i < n && j <= i) ? A[b * a_bs + (int64_t)i * a_ld + j] : 0.f;
+    if (j == i) v[r] += jitter;
   }
-  W[b * w_bs + (int64_t)i * w_ld + j] = v;
+#pragma unroll
+  for (int r = 0; r < kInitRows; ++r)
+    if (i0 + r < n) W[b * w_bs + (int64_t)(i0 + r) * w_ld + j] = v[r];
 }
 
 // zero the strict upper triangle outside the nb x nb diagonal blocks (those are zero-filled by the block kernels)
@@ -50,11 +56,14 @@ __global__ void __launch_bounds__(256)
 zero_upper_kernel(float* __restrict__ L, int64_t ld, int64_t bs, int n, int nb) {
   pdl_enter();
   const int64_t b = blockIdx.z;
-  const int i = blockIdx.y;
-  const int j0 = (i / nb + 1) * nb;
-  const int j = j0 + blockIdx.x * 256 + threadIdx.x;
+  const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= n) return;
-  L[b * bs + (int64_t)i * ld + j] = 0.f;
+  const int i0 = blockIdx.y * kInitRows;
+#pragma unroll
+  for (int r = 0; r < kInitRows; ++r) {
+    const int i = i0 + r;
+    if (i < n && j >= (i / nb + 1) * nb) L[b * bs + (int64_t)i * ld + j] = 0.f;
+  }
 }
 
 static int g_blk_nb = 128;        // diagonal block size of the blocked factorisation
@@ -110,7 +119,7 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     return vargp_trtri(L, l_ld, l_bs, W, w_ld, w_bs, n, batch, stream);
   }
 
-  launch_k(potrf_init_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch)), dim3(256), 0, s, 
+  launch_k(potrf_init_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n, kInitRows), (unsigned)batch)), dim3(256), 0, s, 
       A, a_ld, a_bs, W, w_ld, w_bs, (int)n, jitter);
   int rc = launch_status();
   if (rc) return rc;
@@ -201,7 +210,7 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     }
   }
   if (n > nb) {
-    launch_k(zero_upper_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)n, (unsigned)batch)), dim3(256), 0, s, L, l_ld, l_bs,
+    launch_k(zero_upper_kernel, dim3(dim3((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n, kInitRows), (unsigned)batch)), dim3(256), 0, s, L, l_ld, l_bs,
                                                                                                     (int)n, nb);
     rc = launch_status();
     if (rc) return rc;

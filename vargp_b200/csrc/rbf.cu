@@ -149,7 +149,8 @@ rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64
 // theta_bar[h][d] += sum_{c,i} (-zs zs_bar - zs Gz1) ; theta_bar[h][D] += 2 sum_{c,i} (r1 + r2)
 // grid (D tiles, row tiles over C*P); thread = one d, loops h (outer) and the block's rows (inner).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFinRows = 8;
+constexpr int kFinRows = 8;       // rows held in registers at a time
+constexpr int kFinChunks = 3;     // row chunks per CTA: every CTA issues H x 128 theta_bar atomics, so fewer, fatter CTAs
 constexpr int kFinThreads = 128;
 
 __global__ void __launch_bounds__(kFinThreads)
@@ -159,44 +160,63 @@ rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz
                       float* __restrict__ Zbar, float* __restrict__ theta_bar) {
   pdl_enter();
   const int64_t d = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.y * kFinRows;
-  const int rows = (int)min((int64_t)kFinRows, R - row0);
-  float zacc[kFinRows];
+  const int64_t blk0 = (int64_t)blockIdx.y * kFinRows * kFinChunks;
+  constexpr int kMaxH = 4;          // per-h theta accumulators kept across the chunks when H is small
+  float tsum[kMaxH];
 #pragma unroll
-  for (int r = 0; r < kFinRows; ++r) zacc[r] = 0.f;
-  if (d < D) {
-    for (int64_t h = 0; h < H; ++h) {
-      const float isig = expf(-theta[h * theta_rs + d]);
-      float tacc = 0.f;
+  for (int h = 0; h < kMaxH; ++h) tsum[h] = 0.f;
+  for (int ch = 0; ch < kFinChunks; ++ch) {
+    const int64_t row0 = blk0 + (int64_t)ch * kFinRows;
+    if (row0 >= R) break;
+    const int rows = (int)min((int64_t)kFinRows, R - row0);
+    float zacc[kFinRows];
 #pragma unroll
-      for (int r = 0; r < kFinRows; ++r) {
-        if (r < rows) {
-          const int64_t row = h * R + row0 + r;
-          const float z = zs[row * D + d];
-          const float g1 = Gz1 ? Gz1[row * D + d] : 0.f;
-          const float g2 = Gz2 ? Gz2[row * D + d] : 0.f;
-          const float rr = (r1 ? r1[row] : 0.f) + 2.f * (r2 ? r2[row] : 0.f);
-          const float zb = fmaf(-rr, z, g1 + 2.f * g2);
-          zacc[r] = fmaf(zb, isig, zacc[r]);
-          tacc -= z * (zb + g1);
+    for (int r = 0; r < kFinRows; ++r) zacc[r] = 0.f;
+    if (d < D) {
+      for (int64_t h = 0; h < H; ++h) {
+        const float isig = expf(-theta[h * theta_rs + d]);
+        float tacc = 0.f;
+#pragma unroll
+        for (int r = 0; r < kFinRows; ++r) {
+          if (r < rows) {
+            const int64_t row = h * R + row0 + r;
+            const float z = zs[row * D + d];
+            const float g1 = Gz1 ? Gz1[row * D + d] : 0.f;
+            const float g2 = Gz2 ? Gz2[row * D + d] : 0.f;
+            const float rr = (r1 ? r1[row] : 0.f) + 2.f * (r2 ? r2[row] : 0.f);
+            const float zb = fmaf(-rr, z, g1 + 2.f * g2);
+            zacc[r] = fmaf(zb, isig, zacc[r]);
+            tacc -= z * (zb + g1);
+          }
+        }
+        if (H <= kMaxH) {
+#pragma unroll
+          for (int hh = 0; hh < kMaxH; ++hh)
+            if (hh == h) tsum[hh] += tacc;
+        } else {
+          atomicAdd(theta_bar + h * (D + 1) + d, tacc);
         }
       }
-      atomicAdd(theta_bar + h * (D + 1) + d, tacc);
-    }
 #pragma unroll
-    for (int r = 0; r < kFinRows; ++r)
-      if (r < rows) Zbar[(row0 + r) * D + d] = zacc[r];
-  }
-  if (blockIdx.x == 0 && threadIdx.x < rows) {
-    for (int64_t h = 0; h < H; ++h) {
-      const int64_t row = h * R + row0 + threadIdx.x;
-      atomicAdd(theta_bar + h * (D + 1) + D, 2.f * ((r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f) + (dg ? dg[row] : 0.f)));
+      for (int r = 0; r < kFinRows; ++r)
+        if (r < rows) Zbar[(row0 + r) * D + d] = zacc[r];
     }
+    if (blockIdx.x == 0 && threadIdx.x < rows) {
+      for (int64_t h = 0; h < H; ++h) {
+        const int64_t row = h * R + row0 + threadIdx.x;
+        atomicAdd(theta_bar + h * (D + 1) + D, 2.f * ((r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f) + (dg ? dg[row] : 0.f)));
+      }
+    }
+  }
+  if (d < D && H <= kMaxH) {
+#pragma unroll
+    for (int hh = 0; hh < kMaxH; ++hh)
+      if (hh < H) atomicAdd(theta_bar + hh * (D + 1) + d, tsum[hh]);
   }
 }
 
 // theta_bar[h][d] += sum_j csum[h][j] xs[h][j][d]^2     grid (D tiles, j tiles, H)
-constexpr int kXsRows = 64;
+constexpr int kXsRows = 16;
 __global__ void __launch_bounds__(128)
 rbf_bwd_xside_theta_kernel(const float* __restrict__ xs, const float* __restrict__ csum, int64_t B, int64_t D,
                            float* __restrict__ theta_bar) {
@@ -207,6 +227,7 @@ rbf_bwd_xside_theta_kernel(const float* __restrict__ xs, const float* __restrict
   const int64_t j1 = min(B, j0 + kXsRows);
   if (d >= D) return;
   float acc = 0.f;
+#pragma unroll 8
   for (int64_t j = j0; j < j1; ++j) {
     const float v = xs[(h * B + j) * D + d];
     acc = fmaf(csum[h * B + j] * v, v, acc);
@@ -281,8 +302,8 @@ extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const flo
   if (!zs || !theta || !Zbar || !theta_bar) return VARGP_ERR_ARG;
   if ((Gz1 != nullptr) != (r1 != nullptr) || (Gz2 != nullptr) != (r2 != nullptr)) return VARGP_ERR_ARG;
   const int64_t R = C * P;
-  if (ceil_div(R, kFinRows) > 65535) return VARGP_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows));
+  if (ceil_div(R, kFinRows * kFinChunks) > 65535) return VARGP_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows * kFinChunks));
   launch_k(rbf_bwd_finish_kernel, dim3(grid), dim3(kFinThreads), 0, (cudaStream_t)stream, zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs, H, R,
                                                                          D, Zbar, theta_bar);
   return launch_status();
@@ -293,7 +314,7 @@ extern "C" int vargp_rbf_bwd_xside(const float* xs, const float* csum, const flo
                                    float* theta_bar, float* xbar, void* stream) {
   if (!xs || !csum || !theta || !theta_bar) return VARGP_ERR_ARG;
   if ((xbar != nullptr) != (Gx != nullptr)) return VARGP_ERR_ARG;
-  if (ceil_div(B, kXsRows) > 65535 || H > 65535 || B > 65535 * 64) return VARGP_ERR_UNSUPPORTED;
+  if (ceil_div(B, kXsRows) > 65535 || H > 65535 || B > (int64_t)65535 * kXsRows) return VARGP_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(B, kXsRows), (unsigned)H);
   launch_k(rbf_bwd_xside_theta_kernel, dim3(grid), dim3(128), 0, s, xs, csum, B, D, theta_bar);

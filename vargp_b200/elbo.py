@@ -42,6 +42,7 @@ class _Ctx:
 
 _SIDE = {}
 USE_SIDE_STREAM = os.environ.get('VARGP_STREAMS', '1') != '0'
+KZZ_FIRST = os.environ.get('VARGP_KZZ_FIRST', '1') != '0'
 
 
 class _Fork:
@@ -193,9 +194,18 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   # (2) Gram matrices                                                          [kernels.py:45-56]
   #     the x side and Kzx (minibatch-sized) run on the side stream next to Kzz -> Cholesky -> whitening -> KL -> N
   fork = _Fork(dev)
-  with fork:
-    ops.scale_rows(x, theta, xs, xn)
-    ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
+  side_queued = False
+
+  def queue_side():
+    nonlocal side_queued
+    if not side_queued:
+      side_queued = True
+      with fork:
+        ops.scale_rows(x, theta, xs, xn)
+        ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
+
+  if not KZZ_FIRST:
+    queue_side()
 
   # (3)-(6a) factor stage on this rank's (h, c) rectangles
   L = new(H, C, P, P)
@@ -219,6 +229,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     # W = chol(Kzz + eps I)^-1                                                 [gp_utils.py:5-11]
     ops.chol_inv(Kzz[r], L[r], W[r], JITTER, info.view(H, C)[r].reshape(-1) if Hs * Cs == G else
                  info[h0 * C + c0:h0 * C + c1])
+    # the side branch is queued AFTER the head of the critical chain (Kzz -> Cholesky), so that launch order --
+    # like the stream priorities under graph replay -- hands the SMs to the chain first
+    queue_side()
     # whitened variational parameters (block diagonal)
     Wd = _blocks(W[r], S, M)
     ops.gemm(Wd, LuB[:, c0:c1], T[r], a_tri='lower', b_tri='lower', tag='T=Wss*Lu', zeroed=True)
@@ -237,6 +250,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
              zeroed=True)
     ops.gemm(T[r], T[r].transpose(-1, -2), _blocks(N[r], S, M), beta=1., a_tri='lower', b_tri='upper',
              tag='N+=T*Tt', zeroed=True)
+  queue_side()
   if shard is not None:
     shard.all_gather(Wf, k)
     shard.all_gather(Nf, k)

@@ -12,8 +12,12 @@ device buffers before each replay; the three loss terms come back in static 0-d 
 import torch
 import torch.distributed as dist
 
+import os
+
 from .dist import shard_coef, shard_loss
 from .optim import FlatYogi
+
+USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
 
 
 class ElboStepper:
@@ -72,7 +76,11 @@ class ElboStepper:
     from . import ops as _ops_mod
     ops = _ops_mod.get_ops()
     # warm up on a side stream (allocator pools, lazy inits, cuBLAS-free so nothing else to prime)
-    s = torch.cuda.Stream()
+    # The capture stream has HIGH priority: its kernel nodes inherit it, the nodes of the side branches
+    # (elbo._Fork: the minibatch-sized Kzx / Gz1 GEMMs, a few hundred CTAs each) keep the default, lowest one.  The
+    # block scheduler then hands SMs to the critical chain (Kzz -> Cholesky -> whitening ...: many short kernels of
+    # <= 30..270 CTAs) first, and the side GEMMs fill what is left instead of making the chain queue behind them.
+    s = torch.cuda.Stream(priority=-1 if USE_PRIORITY else 0)
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
       for _ in range(3):
@@ -81,7 +89,7 @@ class ElboStepper:
     torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph()
     n0 = ops.launch_count()
-    with torch.cuda.graph(self.graph):
+    with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._grad_body() if self.world > 1 else self._body()
     self.launches_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
 
