@@ -65,6 +65,14 @@ const char* vargp_strerror(int code);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t vargp_launch_count(void);
 
+/* Step graph with per-node priorities: instantiate a captured cudaGraph_t (`graph`) with
+ * cudaGraphInstantiateFlagUseNodePriority (use_node_priority != 0) so that kernel nodes captured from a
+ * high-priority stream -- the critical chain of the ELBO step -- are scheduled before the default-priority side
+ * branches; launch / destroy the resulting cudaGraphExec_t.  The caller keeps `graph` and its memory pool alive. */
+int vargp_graph_instantiate(void* graph, int use_node_priority, void** exec_out);
+int vargp_graph_launch(void* exec, void* stream);
+int vargp_graph_exec_destroy(void* exec);
+
 int vargp_gemm(const vargp_gemm_t* g, void* stream);
 
 /* tcgen05 / TMA path (3xTF32): same contract as vargp_gemm restricted to K-contiguous operands

@@ -7,7 +7,6 @@ run() { name=$1; shift; env "$@" timeout 100 python bench.py --steps 50 --warmup
 import json; d=json.load(open("$OUT/${TAG}_ab_$name.json")); print("$name", d["value"], "steps/s", d["ms_per_step"], "ms  e2e", d["e2e"]["value"], d["clocks"]["sm_mhz"])
 PY
 }
-run base VARGP_PRIO=0 VARGP_KZZ_FIRST=0
-run kzzfirst VARGP_PRIO=0 VARGP_KZZ_FIRST=1
-run prio VARGP_PRIO=1 VARGP_KZZ_FIRST=1
-run prio_attr VARGP_PRIO=1 VARGP_KZZ_FIRST=1 VARGP_PRIO_ATTR=1
+run torch_replay VARGP_NODE_PRIO=0
+run node_prio VARGP_NODE_PRIO=1
+run node_prio_attr VARGP_NODE_PRIO=1 VARGP_PRIO_ATTR=1

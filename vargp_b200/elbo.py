@@ -60,10 +60,21 @@ class _Fork:
         _SIDE[key] = torch.cuda.Stream(device=dev)
       self.side = _SIDE[key]
     self._ctx = None
+    self._ev = None
+
+  def mark(self):
+    """The side branch depends on what is queued on the current stream UP TO HERE (not up to the point where it
+    is queued): lets the branch be launched after the head of the critical chain without waiting for it."""
+    if self.side is not None:
+      self._ev = torch.cuda.Event()
+      self._ev.record(torch.cuda.current_stream())
 
   def __enter__(self):
     if self.side is not None:
-      self.side.wait_stream(torch.cuda.current_stream())
+      if self._ev is not None:
+        self.side.wait_event(self._ev)
+      else:
+        self.side.wait_stream(torch.cuda.current_stream())
       self._ctx = torch.cuda.stream(self.side)
       self._ctx.__enter__()
     return self
@@ -194,6 +205,8 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   # (2) Gram matrices                                                          [kernels.py:45-56]
   #     the x side and Kzx (minibatch-sized) run on the side stream next to Kzz -> Cholesky -> whitening -> KL -> N
   fork = _Fork(dev)
+  if KZZ_FIRST:
+    fork.mark()                  # the Kzx branch needs theta and the scaled z only
   side_queued = False
 
   def queue_side():

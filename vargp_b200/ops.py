@@ -56,6 +56,9 @@ def _load():
   lib.vargp_launch_count.restype = i64
   lib.vargp_init.argtypes = [ctypes.c_int]
   lib.vargp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
+  lib.vargp_graph_instantiate.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+  lib.vargp_graph_launch.argtypes = [vp, vp]
+  lib.vargp_graph_exec_destroy.argtypes = [vp]
   lib.vargp_gemm_tc.argtypes = [ctypes.POINTER(GemmDesc), vp]
   lib.vargp_tc2_config.argtypes = [i64]
   lib.vargp_tc2_config.restype = i64
@@ -187,6 +190,21 @@ class CudaOps:
 
   def launch_count(self):
     return int(self.lib.vargp_launch_count())
+
+  # -- step graph with per-node priorities ------------------------------------------------------
+  def graph_instantiate(self, raw_graph, use_node_priority=True):
+    """cudaGraph_t (int, e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()) -> cudaGraphExec_t handle."""
+    out = vp()
+    self._check(self.lib.vargp_graph_instantiate(vp(raw_graph), int(bool(use_node_priority)), ctypes.byref(out)),
+                'vargp_graph_instantiate')
+    return out
+
+  def graph_launch(self, exec_handle, stream=None):
+    st = torch.cuda.current_stream() if stream is None else stream
+    self._check(self.lib.vargp_graph_launch(exec_handle, vp(st.cuda_stream)), 'vargp_graph_launch')
+
+  def graph_exec_destroy(self, exec_handle):
+    self.lib.vargp_graph_exec_destroy(exec_handle)
 
   def tc2_config(self, min_tiles=None):
     """Set (or with None query) the tile-count threshold above which GEMMs take the 2-CTA kernel; < 0 disables."""

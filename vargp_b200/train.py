@@ -18,6 +18,11 @@ from .dist import shard_coef, shard_loss
 from .optim import FlatYogi
 
 USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
+# VARGP_NODE_PRIO=1: replay the step graph through libvargp_sm100.so's cudaGraphInstantiateFlagUseNodePriority exec
+# (single-GPU steps).  PyTorch's own instantiation runs every node at the launch stream's priority, which throws the
+# per-node priorities away.  Opt-in: measured on B200 at the Split-MNIST shape it changes nothing (731 vs 734 steps/s;
+# profiles/r1d_timeline_node_prio.txt: the critical chain still queues behind the resident CTAs of the side GEMMs).
+USE_NODE_PRIORITY = os.environ.get('VARGP_NODE_PRIO', '0') != '0'
 
 
 class ElboStepper:
@@ -46,13 +51,38 @@ class ElboStepper:
     self.coef = torch.tensor(shard_coef(beta, n_data, self.global_batch, world_size, self.shard is not None), device=dev)
     self.terms = None
     self.launches_per_step = None
+    self.exec = None             # cudaGraphExec_t with per-node priorities (single-GPU graph mode)
+    self.noise = None            # static noise buffers, refilled eagerly before every launch of `exec`
     gp.sync_errors = False
+
+  def _make_noise(self):
+    """Static buffers for the step's three draws (same shapes, dtype and order as the draws VARGP.loss issues itself:
+    hypers -> u_<t -> likelihood).  A graph launched outside torch.cuda.CUDAGraph.replay() cannot
+    contain torch RNG kernels (replay() is what advances their Philox offsets), so the node-priority exec takes
+    its noise from these buffers and `_draw_noise` refills them on the stream right before each launch."""
+    gp = self.gp
+    dev, dt = self.x.device, gp.z.dtype
+    new = lambda *sh: torch.empty(*sh, device=dev, dtype=dt)
+    C, B = gp.z.size(0), self.x.size(0)
+    H = 1 if gp.kernel.map_est else gp.n_v
+    nz = dict()
+    if not gp.kernel.map_est:
+      nz['eps_theta'] = new(gp.n_v, gp.kernel.log_mean.numel())
+    if gp.n_prev:
+      nz['eps_u'] = new(gp.n_v, H, C, gp.n_prev * gp.M)
+    nz['eps_f'] = new(H, gp.likelihood.n_f, C, B)
+    return nz
+
+  def _draw_noise(self):
+    for k in ('eps_theta', 'eps_u', 'eps_f'):
+      if k in self.noise:
+        self.noise[k].normal_()
 
   def _grad_body(self):
     self.opt.zero_grad()
     self.gp.factor_shard = self.shard
     try:
-      kl_h, kl_u, nll = self.gp.loss(self.x, self.y)
+      kl_h, kl_u, nll = self.gp.loss(self.x, self.y, noise=self.noise)
     finally:
       self.gp.factor_shard = None
     loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
@@ -74,12 +104,16 @@ class ElboStepper:
     all-reduce of the flat gradient buffer and the (two-launch) Yogi step follow it eagerly, which keeps NCCL out
     of the capture at the price of three host calls per step instead of one."""
     from . import ops as _ops_mod
-    ops = _ops_mod.get_ops()
+    ops = self._ops = _ops_mod.get_ops()
     # warm up on a side stream (allocator pools, lazy inits, cuBLAS-free so nothing else to prime)
     # The capture stream has HIGH priority: its kernel nodes inherit it, the nodes of the side branches
     # (elbo._Fork: the minibatch-sized Kzx / Gz1 GEMMs, a few hundred CTAs each) keep the default, lowest one.  The
     # block scheduler then hands SMs to the critical chain (Kzz -> Cholesky -> whitening ...: many short kernels of
     # <= 30..270 CTAs) first, and the side GEMMs fill what is left instead of making the chain queue behind them.
+    node_prio = USE_PRIORITY and USE_NODE_PRIORITY and self.world == 1
+    if node_prio:
+      self.noise = self._make_noise()
+      self._draw_noise()
     s = torch.cuda.Stream(priority=-1 if USE_PRIORITY else 0)
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -87,10 +121,12 @@ class ElboStepper:
         self._body()
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
-    self.graph = torch.cuda.CUDAGraph()
+    self.graph = torch.cuda.CUDAGraph(keep_graph=True) if node_prio else torch.cuda.CUDAGraph()
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._grad_body() if self.world > 1 else self._body()
+    if node_prio:
+      self.exec = ops.graph_instantiate(self.graph.raw_cuda_graph(), use_node_priority=True)
     self.launches_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
 
   def step(self, x, y):
@@ -99,13 +135,26 @@ class ElboStepper:
     self.x.copy_(x, non_blocking=True)
     self.y.copy_(y, non_blocking=True)
     if not self.use_graph:
+      if self.noise is not None:
+        self._draw_noise()
       return self._body()
     if self.graph is None:
       self._capture()      # note: the capture itself does not advance the parameters
-    self.graph.replay()
+    if self.exec is not None:
+      self._draw_noise()
+      self._ops.graph_launch(self.exec)
+    else:
+      self.graph.replay()
     if self.world > 1:
       self._finish()
     return self.terms
+
+  def __del__(self):
+    if getattr(self, 'exec', None) is not None:
+      try:
+        self._ops.graph_exec_destroy(self.exec)
+      except Exception:
+        pass
 
 
 # ------------------------------------------------------------------------------------------------------
