@@ -150,7 +150,7 @@ rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64
 // grid (D tiles, row tiles over C*P); thread = one d, loops h (outer) and the block's rows (inner).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinRows = 8;       // rows held in registers at a time
-constexpr int kFinChunks = 3;     // row chunks per CTA: every CTA issues H x 128 theta_bar atomics, so fewer, fatter CTAs
+constexpr int kFinChunks = 1;     // row chunks per CTA (3 was measured 2x slower at the Split-MNIST shape: the kernel is latency-bound, it needs the CTAs)
 constexpr int kFinThreads = 128;
 
 __global__ void __launch_bounds__(kFinThreads)
