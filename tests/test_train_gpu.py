@@ -78,3 +78,49 @@ def test_train_driver_continual_toy(cuda_ops):
   acc, ent = compute_acc_ent(TensorTask(x, y), gp)
   assert accs[0][0] > 0.8 and accs[1][1] > 0.8 and acc > 0.6 and ent > 0
   assert compute_bwt(torch.tensor(accs)).abs() < 0.5
+
+
+def test_prefetched_inputs_give_the_same_steps(cuda_ops):
+  """step(x, y, prefetch=next) copies the next minibatch on the copy stream while the step runs; the trajectory must be
+  the same as feeding the same pinned batches directly (same graph, same RNG stream)."""
+  from vargp_b200.train import ElboStepper
+  g = torch.Generator().manual_seed(11)
+  xs = torch.rand(4, 256, 784, generator=g).pin_memory()
+  ys = torch.randint(0, 10, (4, 256), generator=g).pin_memory()
+  out = {}
+  for mode in ('direct', 'prefetch'):
+    gp, _, _ = _model()
+    st = ElboStepper(gp, n_data=2560, batch_size=256, beta=1.0, lr=1e-2, use_graph=True)
+    torch.manual_seed(7)
+    vals = []
+    for i in range(12):
+      if mode == 'prefetch':
+        st.step(xs[i % 4], ys[i % 4], prefetch=(xs[(i + 1) % 4], ys[(i + 1) % 4]))
+      else:
+        st.step(xs[i % 4], ys[i % 4])
+      vals.append(st.terms_vec.clone())
+    gp.check_errors()
+    out[mode] = (torch.stack(vals).cpu(), gp.z.detach().clone().cpu())
+    if mode == 'prefetch':
+      assert st._copy_stream is not None
+  # same graph, same noise; a few reductions use float atomics, so equal up to summation order, not bits
+  assert util.relerr(out['prefetch'][0], out['direct'][0]) < 1e-4
+  assert util.relerr(out['prefetch'][1], out['direct'][1]) < 1e-4
+  assert util.relerr(out['direct'][0][1:], out['direct'][0][:-1]) > 1e-4      # and the steps really differ from each other
+  assert out['direct'][0].shape == (12, 3) and torch.isfinite(out['direct'][0]).all()
+
+
+def test_predict_at_notebook_sizes(cuda_ops):
+  """The paper's evaluation recipe (notebooks: n_var_samples = 20 hyper samples, n_f = 50 likelihood samples) on a
+  Split-MNIST-shaped model: predict() vs the fp64 CPU oracle, 1e-5 absolute."""
+  from oracle import vargp_oracle as orc
+  kw = dict(C=10, D=784, M=20, t=2, B=96, H=20, F=50, sigma=10., seed=17)
+  params, prev, x, y, noise = orc.make_case(dtype=torch.float32, **kw)
+  gp = util.build_model(params, prev, 20, 50, {}, 'cuda', torch.float32)
+  with torch.no_grad():
+    probs = gp.predict(x.cuda(), noise={k: v.cuda() for k, v in noise.items()})
+  p64, prev64, x64, _, n64 = orc.make_case(dtype=torch.float64, **kw)
+  ref = orc.predict(p64, prev64, x64, n64, n_v=20)
+  assert tuple(probs.shape) == (96, 10)
+  assert (probs.double().cpu() - ref).abs().max().item() < 1e-5
+  assert (probs.sum(-1) - 1).abs().max().item() < 1e-5

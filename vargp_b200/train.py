@@ -51,6 +51,9 @@ class ElboStepper:
     self.coef = torch.tensor(shard_coef(beta, n_data, self.global_batch, world_size, self.shard is not None), device=dev)
     self.terms = None
     self.launches_per_step = None
+    self.terms_vec = None        # (kl_hypers, kl_u, nll) of the last step as one (3,) device tensor
+    self._pf = None              # prefetch state: (x_src, y_src, x_staging, y_staging, ready event)
+    self._copy_stream = None
     self.exec = None             # cudaGraphExec_t with per-node priorities (single-GPU graph mode)
     self.noise = None            # static noise buffers, refilled eagerly before every launch of `exec`
     gp.sync_errors = False
@@ -87,7 +90,9 @@ class ElboStepper:
       self.gp.factor_shard = None
     loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
     loss.backward()
-    return kl_h.detach(), kl_u.detach(), nll.detach()
+    terms = (kl_h.detach(), kl_u.detach(), nll.detach())
+    self.terms_vec = torch.stack(terms)          # the three terms as one (3,) tensor: a single D2H for loggers
+    return terms
 
   def _finish(self):
     if self.world > 1:
@@ -125,29 +130,67 @@ class ElboStepper:
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._grad_body() if self.world > 1 else self._body()
+    self._graph_terms_vec = self.terms_vec      # static output of the graph
     if node_prio:
       self.exec = ops.graph_instantiate(self.graph.raw_cuda_graph(), use_node_priority=True)
     self.launches_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
 
-  def step(self, x, y):
+  def _load_inputs(self, x, y):
+    """Inputs of this step into the static buffers: from the staging buffers if (x, y) are the tensors announced
+    by the previous call's `prefetch` (their H2D copy ran on the copy stream beside the previous step), else by a
+    direct copy."""
+    pf, self._pf = self._pf, None
+    if pf is not None and pf[0].data_ptr() == x.data_ptr() and pf[0].shape == x.shape and pf[1].data_ptr() == y.data_ptr():
+      cur = torch.cuda.current_stream()
+      cur.wait_event(pf[4])
+      self.x.copy_(pf[2], non_blocking=True)
+      self.y.copy_(pf[3], non_blocking=True)
+      self._staging_free.record(cur)
+    else:
+      self.x.copy_(x, non_blocking=True)
+      self.y.copy_(y, non_blocking=True)
+
+  def _prefetch(self, x, y):
+    if self._copy_stream is None:
+      self._copy_stream = torch.cuda.Stream()
+      self._xs, self._ys = torch.empty_like(self.x), torch.empty_like(self.y)
+      self._staging_free = torch.cuda.Event()
+      self._staging_free.record(torch.cuda.current_stream())
+    cs = self._copy_stream
+    cs.wait_event(self._staging_free)              # the previous step has read the staging buffers
+    with torch.cuda.stream(cs):
+      self._xs.copy_(x, non_blocking=True)
+      self._ys.copy_(y, non_blocking=True)
+      ready = torch.cuda.Event()
+      ready.record(cs)
+    self._pf = (x, y, self._xs, self._ys, ready)
+
+  def step(self, x, y, prefetch=None):
     """One optimisation step on the minibatch (x, y) (device or pinned-host tensors).  Returns the three
-    loss terms as 0-d device tensors (valid until the next call)."""
-    self.x.copy_(x, non_blocking=True)
-    self.y.copy_(y, non_blocking=True)
+    loss terms as 0-d device tensors (valid until the next call); `terms_vec` holds them as one (3,) tensor.
+
+    prefetch=(x_next, y_next): the NEXT call's inputs (pinned host tensors); their host-to-device copy is issued on
+    a copy stream right after this step has been launched, so it overlaps the step instead of preceding the next
+    (the caller must leave those host tensors untouched until then, as with any non_blocking copy)."""
+    self._load_inputs(x, y)
     if not self.use_graph:
       if self.noise is not None:
         self._draw_noise()
-      return self._body()
-    if self.graph is None:
-      self._capture()      # note: the capture itself does not advance the parameters
-    if self.exec is not None:
-      self._draw_noise()
-      self._ops.graph_launch(self.exec)
+      out = self._body()
     else:
-      self.graph.replay()
-    if self.world > 1:
-      self._finish()
-    return self.terms
+      if self.graph is None:
+        self._capture()      # note: the capture itself does not advance the parameters
+      if self.exec is not None:
+        self._draw_noise()
+        self._ops.graph_launch(self.exec)
+      else:
+        self.graph.replay()
+      if self.world > 1:
+        self._finish()
+      out, self.terms_vec = self.terms, self._graph_terms_vec
+    if prefetch is not None:
+      self._prefetch(*prefetch)
+    return out
 
   def __del__(self):
     if getattr(self, 'exec', None) is not None:
