@@ -98,3 +98,25 @@ def test_dkl_fused_schedule_agrees_with_composed_fp64(emu_ops):
       assert g_f[k].norm() < 1e-10 * g_f['kernel.phi.4.weight'].norm()
     else:
       assert util.relerr(g_f[k], g_c[k]) < 1e-10, k
+
+
+def test_compute_q_and_pf_diag_methods_match_oracle(emu_ops):
+  """The reference's two intermediate methods (var_gp/vargp.py:35-113) keep their signatures and values: moments of
+  q(u_<t), q(u_<=t), the stacked inducing inputs and the predictive marginal, against the oracle in fp64."""
+  from oracle import vargp_oracle as orc
+  rec = util.load_golden('odd_t2')
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float64)
+  gp = util.build_model(params, prev, n_v, F, flags, 'cpu', torch.float64)
+  theta = orc.sample_hypers(params['log_mean'], params['log_logvar'], noise['eps_theta'])
+  cache = dict()
+  with torch.no_grad():
+    out = gp.compute_q(theta, cache=cache)
+    f_mean, f_var = gp.compute_pf_diag(theta, x, *out[2:])
+  prevp = [dict(z=p['z'], u_mean=p['u_mean'], u_tril=orc.vec2tril(p['u_tril_vec'])) for p in prev]
+  ocache = dict()
+  ref = orc.compute_q(theta, prevp, params['z'], params['u_mean'], params['u_tril_vec'], cache=ocache)
+  for a, b in zip(out, ref):
+    assert a.shape == b.shape and (a - b).abs().max() < 1e-10
+  for k in ('Lz_lt', 'Lz_lt_Kz_lt_z_t'):
+    assert (cache[k] - ocache[k]).abs().max() < 1e-10
+  assert (f_mean - rec['f64']['f_mean']).abs().max() < 1e-9 and (f_var - rec['f64']['f_var']).abs().max() < 1e-9

@@ -109,6 +109,20 @@ class VARGP(nn.Module):
                             f'(leading minor of order {bad} is not positive-definite)')
 
   # -- reference API --------------------------------------------------------------------------
+  def compute_q(self, theta, cache=None):
+    """Autoregressive variational distributions q(u_<t | theta), q(u_<=t | theta)   (var_gp/vargp.py:35-88).
+    theta (n_hypers, D+1) -> mu_lt, S_lt, mu_leq_t, S_leq_t, z_leq_t; `cache` receives Lz_lt, Lz_lt_Kz_lt_z_t.
+    Reference-order composed path (the training step never materialises these: elbo.py works in whitened space)."""
+    if not self.n_prev:
+      raise ValueError('compute_q needs prev_params (the reference indexes prev_params[0], vargp.py:52)')
+    from .composed import _compute_q
+    return _compute_q(self, theta, cache=cache)
+
+  def compute_pf_diag(self, theta, x, mu_leq_t, S_leq_t, z_leq_t, cache=None):
+    """Diagonal of p(f) = int p(f | u_<=t) q(u_<=t)   (var_gp/vargp.py:90-113) -> f_mean, f_var (n_hypers, C, B)."""
+    from .composed import _compute_pf_diag
+    return _compute_pf_diag(self, theta, x, mu_leq_t, S_leq_t, z_leq_t, cache=cache)
+
   def forward(self, x, loss_cache=False, noise=None):
     """x (B, in_size) -> pred_mu, pred_var (n_hypers, out_size, B)   (var_gp/vargp.py:115-175).
 
