@@ -120,3 +120,22 @@ def test_compute_q_and_pf_diag_methods_match_oracle(emu_ops):
   for k in ('Lz_lt', 'Lz_lt_Kz_lt_z_t'):
     assert (cache[k] - ocache[k]).abs().max() < 1e-10
   assert (f_mean - rec['f64']['f_mean']).abs().max() < 1e-9 and (f_var - rec['f64']['f_var']).abs().max() < 1e-9
+
+
+@pytest.mark.parametrize('flag', ['STACK_CLASSES', 'V_SIDE', 'both'])
+@pytest.mark.parametrize('name', ['mnist_t3', 'odd_t2', 'toy_t0'])
+def test_optional_schedules_are_the_same_function(name, flag, emu_ops, monkeypatch):
+  """The opt-in schedule variants of elbo.py (class-stacked Kzx / Gz1 products, V on the side branch) compute the same
+  ELBO terms and gradients as the reference fixtures."""
+  from vargp_b200 import elbo
+  for f in (('STACK_CLASSES', 'V_SIDE') if flag == 'both' else (flag,)):
+    monkeypatch.setattr(elbo, f, True)
+  rec = util.load_golden(name)
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float64)
+  ref = rec['f64']
+  gp = util.build_model(params, prev, n_v, F, flags, 'cpu', torch.float64)
+  terms, grads = util.run_model(gp, x, y, noise, ref['beta'], ref['Ntot'])
+  for k in ('kl_u', 'nll', 'total'):
+    assert util.relerr(terms[k], ref[k]) < 1e-8, k
+  for k in util.GRAD_KEYS:
+    assert util.relerr(grads[k], ref['grads'][k]) < 1e-7, k

@@ -43,6 +43,14 @@ class _Ctx:
 _SIDE = {}
 USE_SIDE_STREAM = os.environ.get('VARGP_STREAMS', '1') != '0'
 KZZ_FIRST = os.environ.get('VARGP_KZZ_FIRST', '1') != '0'
+# Opt-in schedule experiments (semantics covered by the CPU host-schedule tests; not yet measured on a B200):
+#   VARGP_STACK_CLASSES=1  x is shared by all classes, so Kzx and Gz1 = (Kxbar . Kzx) xs are ONE (C P) x B / (C P) x D
+#                          product per hyper sample instead of C products with P rows each: at P = 300 that is 24
+#                          instead of 30 row tiles of 128 (the per-class tiling pads 300 rows to 384).
+#   VARGP_V_SIDE=1         V = W Kzx on the side stream right behind Kzx (waiting for an event recorded after the
+#                          factorisation), so that it overlaps the T / nu / KL / N chain instead of following it.
+STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '0') != '0'
+V_SIDE = os.environ.get('VARGP_V_SIDE', '0') != '0'
 
 
 class _Fork:
@@ -88,6 +96,13 @@ class _Fork:
   def join(self):
     if self.side is not None:
       torch.cuda.current_stream().wait_stream(self.side)
+
+  def after_main(self):
+    """Make what is queued on the side stream from now on also wait for everything queued on the current stream."""
+    if self.side is not None:
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream())
+      self.side.wait_event(ev)
 
 
 def _zeros_many(dev, dt, *shapes):
@@ -215,7 +230,11 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
       side_queued = True
       with fork:
         ops.scale_rows(x, theta, xs, xn)
-        ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
+        if STACK_CLASSES:
+          ops.rbf_gram(zs.view(H, 1, C * P, D), zn.view(H, 1, C * P), xs.view(H, 1, B, D), xn.view(H, 1, B), theta,
+                       Kzx.view(H, 1, C * P, B), False, tag='Kzx')
+        else:
+          ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
 
   if not KZZ_FIRST:
     queue_side()
@@ -227,6 +246,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   nuf, nu = _pairs(G, P, P, dev=dev, dt=dt, slots=slots)
   W, N, nu = W.view(H, C, P, P), N.view(H, C, P, P), nu.view(H, C, P)
   T = new(H, C, S, M, M)
+  # V_SIDE: only when one rectangle covers every pair (unsharded), so that W is complete after its chol_inv
+  v_early = V_SIDE and shard is None and len(rects) == 1
+  V_early = new(H, C, P, B) if v_early else None
   if dt == torch.float32:       # Cholesky status words and the KL accumulator share one zero-filled buffer
     zb = torch.zeros(G + 1, device=dev, dtype=dt)
     info, kl0 = zb[:G].view(torch.int32), zb[G]
@@ -245,6 +267,10 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     # the side branch is queued AFTER the head of the critical chain (Kzz -> Cholesky), so that launch order --
     # like the stream priorities under graph replay -- hands the SMs to the chain first
     queue_side()
+    if v_early:
+      fork.after_main()                        # W is complete
+      with fork:
+        ops.gemm(W, Kzx, V_early, a_tri='lower', tag='V=W*Kzx', zeroed=True)
     # whitened variational parameters (block diagonal)
     Wd = _blocks(W[r], S, M)
     ops.gemm(Wd, LuB[:, c0:c1], T[r], a_tri='lower', b_tri='lower', tag='T=Wss*Lu', zeroed=True)
@@ -270,9 +296,10 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     shard.all_gather(nuf, k)
 
   # (6b) predictive marginal                                                   [gp_utils.py:150-191]
-  V, NV = new(H, C, P, B), new(H, C, P, B)
+  V, NV = (V_early if v_early else new(H, C, P, B)), new(H, C, P, B)
   fork.join()
-  ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx', zeroed=True)
+  if not v_early:
+    ops.gemm(W, Kzx, V, a_tri='lower', tag='V=W*Kzx', zeroed=True)
   ops.gemm(N, V, NV, tag='NV=N*V')
   f_mean, f_var = new(H, C, B), new(H, C, B)
   ops.marginal_reduce(V, NV, nu, theta, f_mean, f_var)
@@ -327,7 +354,10 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     with fork:
       ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
-      ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
+      if STACK_CLASSES:
+        ops.gemm(Kxbar.view(H, 1, C * P, B), xs.view(H, 1, B, D), Gz1.view(H, 1, C * P, D), tag='Gz1=Wk1*xs')
+      else:
+        ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
       if need_x_grad:
         ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
     # minibatch sums for every pair:  Wbar = tril(Vbar Kzx^T),  G = Nbar = sum_b gv_b V_b V_b^T (lower),  nubar = V gm
