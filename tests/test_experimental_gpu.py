@@ -1,0 +1,78 @@
+"""Opt-in paths written at the end of round 1 WITHOUT GPU time left to run them (compile-checked only): the
+128 x 64-tile two-CTAs-per-SM GEMM variant (vargp_tcs_config) and the optional schedules of elbo.py.  They are off by
+default in the product; these tests only run with VARGP_EXPERIMENTAL=1 so that an unproven kernel cannot take the
+regular `-m gpu` suite down:
+
+    VARGP_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu
+"""
+import os
+
+import pytest
+import torch
+
+from tests import util
+from tests.emu_ops import EmuOps
+from tests.test_gemm_tc_gpu import make, relerr, rnd
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('VARGP_EXPERIMENTAL', '0') == '0', reason='set VARGP_EXPERIMENTAL=1')]
+EMU = EmuOps()
+
+
+@pytest.fixture
+def tcs_ops(cuda_ops):
+  old = cuda_ops.tcs_config(1 << 40)          # every non-tc2 problem takes the small-shape variant
+  yield cuda_ops
+  cuda_ops.tcs_config(old)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 64, 32), (128, 128, 96), (256, 384, 128), (60, 512, 60), (300, 300, 300),
+                                   (300, 512, 300), (132, 68, 44), (300, 784, 512), (64, 64, 784)])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_tcs_gemm_majors(tcs_ops, M, N, K, ta, tb):
+  A, B, Ad, Bd = make((2,), M, N, K, ta, tb)
+  Cd = torch.full((2, M, N), float('nan'), device='cuda')
+  n0 = tcs_ops.tcs_launch_count()
+  tcs_ops.gemm(Ad, Bd, Cd)
+  assert tcs_ops.tcs_launch_count() == n0 + 1, 'small-shape variant was not taken'
+  assert relerr(Cd, A @ B) < 1e-6
+
+
+@pytest.mark.parametrize('kw', [
+  dict(a_tri='lower'), dict(a_tri='upper', ta=True), dict(b_tri='lower'), dict(a_tri='lower', b_tri='upper', tb=True, c_tri='lower'),
+  dict(c_tri='lower', beta=1.0, tb=True), dict(c_tri='upper', alpha=-0.5), dict(beta=0.5, alpha=2.0)])
+def test_tcs_gemm_flags(tcs_ops, kw):
+  kw = dict(kw)
+  ta, tb = kw.pop('ta', False), kw.pop('tb', False)
+  n = 300
+  A, B, Ad, Bd = make((3, 2), n, n, n, ta, tb)
+  for t64, td, tri in ((A, Ad, kw.get('a_tri')), (B, Bd, kw.get('b_tri'))):
+    if tri:
+      mask = torch.ones(n, n).tril(-1).bool() if tri == 'upper' else torch.ones(n, n).triu(1).bool()
+      t64.masked_fill_(mask, 0.0)
+      td.masked_fill_(mask.cuda(), 0.0)
+  C0 = rnd(3, 2, n, n, seed=3)
+  C64 = C0.clone()
+  EMU.gemm(A, B, C64, **kw)
+  Cd = C0.to('cuda', torch.float32)
+  n0 = tcs_ops.tcs_launch_count()
+  tcs_ops.gemm(Ad, Bd, Cd, zeroed=True, **kw)
+  assert tcs_ops.tcs_launch_count() == n0 + 1
+  assert relerr(Cd, C64) < 1e-6, kw
+
+
+@pytest.mark.parametrize('name', ['mnist_t3', 'odd_t2', 'toy_t1'])
+def test_model_parity_on_tcs_and_optional_schedules(name, tcs_ops, monkeypatch):
+  from vargp_b200 import elbo
+  monkeypatch.setattr(elbo, 'STACK_CLASSES', True)
+  monkeypatch.setattr(elbo, 'V_SIDE', True)
+  rec = util.load_golden(name)
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float32)
+  r64 = rec['f64']
+  gp = util.build_model(params, prev, n_v, F, flags, 'cuda', torch.float32)
+  terms, grads = util.run_model(gp, x, y, noise, r64['beta'], r64['Ntot'])
+  tol = 1e-4 if not name.startswith('toy') else 5e-3
+  for k in ('kl_u', 'nll', 'total'):
+    assert util.relerr(terms[k], r64[k]) < tol, k
+  for k in util.GRAD_KEYS:
+    assert util.relerr(grads[k], r64['grads'][k]) < 10 * tol, k

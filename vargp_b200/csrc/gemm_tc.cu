@@ -22,28 +22,47 @@
 //
 // Roofline: tensor pipe (3 TF32 MMAs per product); the split doubles the smem footprint of a slab instead of
 // the HBM/L2 traffic.  Algorithmic flops per launch: 2*M*N*K*batch (x 1/2 per triangular flag).
+//
+// Two instantiations of the same kernel:
+//   <128, 3, 1>  128 x 128 tiles, 3 stages, 192 KiB of shared memory, one CTA per SM                (the default)
+//   < 64, 2, 2>  128 x  64 tiles, 2 stages,  96 KiB, 256 TMEM columns, <= 72 registers: TWO CTAs per SM, so that the
+//                ramp / store phases of one overlap the MMA phase of the other and grids of 150..300 tiles fit one
+//                wave (the P x P products of the Split-MNIST-shaped step are 180..270 tiles of 128 x 128: two waves
+//                for 1.2..1.8 waves of work).  OPT-IN (vargp_tcs_config / VARGP_TCS_MAX_CTAS): written at the end of
+//                round 1 without GPU time left; not yet run on hardware.
 #include "tc_common.cuh"
 
 namespace vargp {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 3;
+constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 448;                                  // 14 warps: TMA, MMA, 4 split, 8 epilogue
-constexpr int TC_SMEM_BYTES = 4 * TC_STAGES * TC_TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_TMEM_COLS = 512;                                // main0 | main1 | lo | (unused)
+
+template <int BN, int STAGES>
+struct TcCfg {
+  static constexpr int B_TILE = BN * TC_BK * 4;                  // bytes of one B slab (TC_TILE_BYTES for the A slab)
+  static constexpr int SMEM_BYTES = STAGES * 2 * (TC_TILE_BYTES + B_TILE) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN == 128 ? 512 : 256;        // main0 | main1 | lo | (unused), BN columns each
+  static constexpr int EC = BN / 2;                              // output columns per epilogue warp
+};
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int TC_BN, int TC_STAGES, int MINB>
+__global__ void __launch_bounds__(TC_THREADS, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcCfg<TC_BN, TC_STAGES>;
+  constexpr int B_TILE = Cfg::B_TILE;
+  constexpr int TC_TMEM_COLS = Cfg::TMEM_COLS;
+  constexpr int EC = Cfg::EC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA_hi = smem;
   uint8_t* sA_lo = sA_hi + TC_STAGES * TC_TILE_BYTES;
   uint8_t* sB_hi = sA_lo + TC_STAGES * TC_TILE_BYTES;
-  uint8_t* sB_lo = sB_hi + TC_STAGES * TC_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB_lo + TC_STAGES * TC_TILE_BYTES);
+  uint8_t* sB_lo = sB_hi + TC_STAGES * B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB_lo + TC_STAGES * B_TILE);
   uint64_t* full_bar = bars;                      // TMA landed
   uint64_t* conv_bar = bars + TC_STAGES;          // hi/lo split done
   uint64_t* empty_bar = bars + 2 * TC_STAGES;     // MMAs that read the stage retired
@@ -114,10 +133,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], 2 * TC_TILE_BYTES);
+        mbar_expect_tx(&full_bar[s], TC_TILE_BYTES + B_TILE);
         const int k0 = (kb_lo + it) * TC_BK;
         uint8_t* da = sA_hi + s * TC_TILE_BYTES;
-        uint8_t* db = sB_hi + s * TC_TILE_BYTES;
+        uint8_t* db = sB_hi + s * B_TILE;
         if (!p.a_mn) {
           tma_load_5d(&tmA, &full_bar[s], da, k0, (int)m0, ca2, ca1, ca0);
         } else {
@@ -125,10 +144,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = 0; c < 4; ++c) tma_load_5d(&tmA, &full_bar[s], da + c * 4096, (int)m0 + 32 * c, k0, ca2, ca1, ca0);
         }
         if (!p.b_mn) {
-          tma_load_5d(&tmB, &full_bar[s], db, k0, (int)n0, cb2, cb1, cb0);
+          tma_load_5d(&tmB, &full_bar[s], db, k0, (int)n0, cb2, cb1, cb0);       // box of TC_BN rows (make_map)
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tma_load_5d(&tmB, &full_bar[s], db + c * 4096, (int)n0 + 32 * c, k0, cb2, cb1, cb0);
+          for (int c = 0; c < TC_BN / 32; ++c)
+            tma_load_5d(&tmB, &full_bar[s], db + c * 4096, (int)n0 + 32 * c, k0, cb2, cb1, cb0);
         }
       }
     }
@@ -146,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(sA_hi + s * TC_TILE_BYTES), a_lo = smem_u32(sA_lo + s * TC_TILE_BYTES);
-        const uint32_t b_hi = smem_u32(sB_hi + s * TC_TILE_BYTES), b_lo = smem_u32(sB_lo + s * TC_TILE_BYTES);
+        const uint32_t b_hi = smem_u32(sB_hi + s * B_TILE), b_lo = smem_u32(sB_lo + s * B_TILE);
         const uint32_t t_main = tmem_base + (uint32_t)(buf * TC_BN), t_lo = tmem_base + 2u * TC_BN;
 #pragma unroll
         for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -181,19 +201,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (it == 0 && t == 0) TC_STAMP(2);
       float4* ah = reinterpret_cast<float4*>(sA_hi + s * TC_TILE_BYTES);
       float4* al = reinterpret_cast<float4*>(sA_lo + s * TC_TILE_BYTES);
-      float4* bh = reinterpret_cast<float4*>(sB_hi + s * TC_TILE_BYTES);
-      float4* bl = reinterpret_cast<float4*>(sB_lo + s * TC_TILE_BYTES);
+      float4* bh = reinterpret_cast<float4*>(sB_hi + s * B_TILE);
+      float4* bl = reinterpret_cast<float4*>(sB_lo + s * B_TILE);
       // kind::tf32 ignores the 13 low mantissa bits, so the RAW slab is the `hi` operand as it landed; only
       // lo = x - trunc_tf32(x) is written (8 B instead of 12 B of shared-memory traffic per element)
+      if constexpr (TC_BN == 128) {
 #pragma unroll 4
-      for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
-        const int idx = e * 128 + t;
-        const float4 va = ah[idx], vb = bh[idx];
-        float4 l;
-        l.x = tf32_lo_of(va.x); l.y = tf32_lo_of(va.y); l.z = tf32_lo_of(va.z); l.w = tf32_lo_of(va.w);
-        al[idx] = l;
-        l.x = tf32_lo_of(vb.x); l.y = tf32_lo_of(vb.y); l.z = tf32_lo_of(vb.z); l.w = tf32_lo_of(vb.w);
-        bl[idx] = l;
+        for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
+          const int idx = e * 128 + t;
+          const float4 va = ah[idx], vb = bh[idx];
+          float4 l;
+          l.x = tf32_lo_of(va.x); l.y = tf32_lo_of(va.y); l.z = tf32_lo_of(va.z); l.w = tf32_lo_of(va.w);
+          al[idx] = l;
+          l.x = tf32_lo_of(vb.x); l.y = tf32_lo_of(vb.y); l.z = tf32_lo_of(vb.z); l.w = tf32_lo_of(vb.w);
+          bl[idx] = l;
+        }
+      } else {
+#pragma unroll 4
+        for (int e = 0; e < TC_TILE_BYTES / 16 / 128; ++e) {
+          const int idx = e * 128 + t;
+          const float4 va = ah[idx];
+          float4 l;
+          l.x = tf32_lo_of(va.x); l.y = tf32_lo_of(va.y); l.z = tf32_lo_of(va.z); l.w = tf32_lo_of(va.w);
+          al[idx] = l;
+        }
+#pragma unroll 4
+        for (int e = 0; e < B_TILE / 16 / 128; ++e) {
+          const int idx = e * 128 + t;
+          const float4 vb = bh[idx];
+          float4 l;
+          l.x = tf32_lo_of(vb.x); l.y = tf32_lo_of(vb.y); l.z = tf32_lo_of(vb.z); l.w = tf32_lo_of(vb.w);
+          bl[idx] = l;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
       __syncwarp();
@@ -213,13 +252,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e_col = p.e_col + i0 * p.e_col_bs[0] + i1 * p.e_col_bs[1] + i2 * p.e_col_bs[2];
       if (m < p.M) rown = 0.5f * e_row[m];
     }
-    float acc[64];
+    float acc[EC];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64);
+    for (int j = 0; j < EC; ++j) acc[j] = 0.f;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * EC);
     auto drain = [&](uint32_t taddr) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < EC / 32; ++c) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -265,8 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_major = p.c_cs == 1;
       const bool accum = p.beta != 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int nc0 = (int)n0 + half * 64 + c * 32;
+      for (int c = 0; c < EC / 32; ++c) {
+        const int nc0 = (int)n0 + half * EC + c * 32;
         if (nc0 >= Ni || mrow >= Mi) break;                                    // warp-uniform
         if (row_major) {
           __syncwarp();
@@ -360,6 +399,10 @@ bool tc2_wants(const vargp_gemm_t* g);
 
 using namespace vargp;
 
+// small-shape variant (128 x 64 tiles, two CTAs per SM): used when the 128 x 128 grid would have at most this many CTAs
+static int64_t g_tcs_max_ctas = -1;            // < 0: off (default)
+static int64_t g_tcs_launches = 0;
+
 int vargp_tc_init() {
   if (g_tc_ready) return 0;
   void* fn = nullptr;
@@ -367,12 +410,26 @@ int vargp_tc_init() {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return e != cudaSuccess ? (int)e : VARGP_ERR_NOT_INIT;
   g_encode = (EncodeTiledFn)fn;
-  e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, 2>::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  const char* env = getenv("VARGP_TCS_MAX_CTAS");
+  if (env) g_tcs_max_ctas = atoll(env);
   int rc = tc2_init();
   if (rc) return rc;
   g_tc_ready = true;
   return 0;
+}
+
+/* 128 x 64-tile, two-CTAs-per-SM variant of the 1-CTA kernel: problems whose 128 x 128 grid has at most `max_ctas` CTAs
+ * take it; < 0 disables it (default), INT64_MIN only queries.  Returns the previous setting. */
+extern "C" int64_t vargp_tcs_config(int64_t max_ctas) {
+  const int64_t old = g_tcs_max_ctas;
+  if (max_ctas != INT64_MIN) g_tcs_max_ctas = max_ctas;
+  return old;
 }
 
 extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
@@ -402,20 +459,32 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   p.a_mn = (a_k && !(a_mn && g->K == 1)) ? 0 : 1;
   p.b_mn = (b_k && !(b_mn && g->K == 1)) ? 0 : 1;
 
+  const int64_t ctas128 = ceil_div(g->N, 128) * ceil_div(g->M, TC_BM) * nbatch;
+  const bool big = tc2_wants(g);
+  const bool small = !big && g_tcs_max_ctas >= 0 && ctas128 <= g_tcs_max_ctas;
+
   alignas(64) CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->M, g->K, g->a_rs, g->a_cs, g->nb, g->a_bs, p.a_mn, p.a_b);
   if (rc) return rc;
   // B(k, n): "rows" of the operand are n; row stride = b_cs, k stride = b_rs
-  rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b);
+  rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b, small ? 64 : TC_ROWS);
   if (rc) return rc;
 
   // large problems: persistent 2-CTA kernel with 256 x 256 tiles (gemm_tc2.cu)
-  if (tc2_wants(g)) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
+  if (big) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
 
-  dim3 grid((unsigned)ceil_div(g->N, TC_BN), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
-  launch_k(gemm_tc_kernel, dim3(grid), dim3(TC_THREADS), TC_SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
+  if (small) {
+    dim3 grid((unsigned)ceil_div(g->N, 64), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
+    launch_k(gemm_tc_kernel<64, 2, 2>, dim3(grid), dim3(TC_THREADS), TcCfg<64, 2>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
+    ++g_tcs_launches;
+    return launch_status();
+  }
+  dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
+  launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
   return launch_status();
 }
+
+extern "C" int64_t vargp_tcs_launch_count(void) { return g_tcs_launches; }
 
 /* profiling aid: device buffer of >= 8 int64 that CTA (0,0,0) of every following vargp_gemm_tc launch (1-CTA kernel)
  * fills with clock64() stamps: entry, setup done, first slab landed, first slab issued, first partial sum ready,

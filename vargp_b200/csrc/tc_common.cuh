@@ -110,8 +110,9 @@ extern EncodeTiledFn g_encode;
 extern bool g_tc_ready;
 
 // operand (rows x K) described by (row stride rs, k stride cs): build a 5-D map (inner, outer, b2, b1, b0)
+// box_rows: operand rows per TMA box of a K-contiguous operand (an M/N-contiguous one is fetched in 32-row chunks)
 inline int make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K, int64_t rs, int64_t cs,
-                    const int64_t* nb, const int64_t* bs, bool mn_major, int32_t* use_b) {
+                    const int64_t* nb, const int64_t* bs, bool mn_major, int32_t* use_b, int box_rows = TC_ROWS) {
   cuuint64_t dims[5];
   cuuint64_t strides[4];
   cuuint32_t box[5] = {32, 1, 1, 1, 1};
@@ -119,7 +120,7 @@ inline int make_map(CUtensorMap* tm, const float* base, int64_t rows, int64_t K,
   if (!mn_major) {            // K contiguous: dims (K, rows)
     dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
     strides[0] = (cuuint64_t)rs * 4;
-    box[1] = TC_ROWS;
+    box[1] = (cuuint32_t)box_rows;
   } else {                    // rows (M or N) contiguous: dims (rows, K)
     dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
     strides[0] = (cuuint64_t)cs * 4;

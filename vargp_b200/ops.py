@@ -63,6 +63,9 @@ def _load():
   lib.vargp_tc2_config.argtypes = [i64]
   lib.vargp_tc2_config.restype = i64
   lib.vargp_tc2_launch_count.restype = i64
+  lib.vargp_tcs_config.argtypes = [i64]
+  lib.vargp_tcs_config.restype = i64
+  lib.vargp_tcs_launch_count.restype = i64
   lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
@@ -212,6 +215,14 @@ class CudaOps:
 
   def tc2_launch_count(self):
     return int(self.lib.vargp_tc2_launch_count())
+
+  def tcs_config(self, max_ctas=None):
+    """Set (or with None query) the CTA-count threshold below which GEMMs take the 128 x 64-tile, two-CTAs-per-SM
+    variant of the 1-CTA kernel; < 0 disables it (default)."""
+    return int(self.lib.vargp_tcs_config(-2 ** 63 if max_ctas is None else int(max_ctas)))
+
+  def tcs_launch_count(self):
+    return int(self.lib.vargp_tcs_launch_count())
 
   # -- GEMM -----------------------------------------------------------------------------------
   def _desc(self, A, B, C, alpha, beta, a_tri, b_tri, c_tri):
