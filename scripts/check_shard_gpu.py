@@ -6,7 +6,7 @@ import os, sys, time, json
 import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests import util
+import bench
 from vargp_b200.synthetic import make_case
 from vargp_b200.dist import shard_coef
 from vargp_b200.elbo import FactorShard
@@ -28,7 +28,7 @@ sl = slice(rank * B, (rank + 1) * B)
 nz = {k: v.cuda() for k, v in dict(noise, eps_f=noise['eps_f'][..., sl].contiguous()).items()}
 res = {}
 for mode in ('replicated', 'sharded'):
-  gp = util.build_model(params, prev, 3, 10, {}, 'cuda', torch.float32)
+  gp = bench.build_gpu_model(params, prev, torch.device('cuda'))
   gp.sync_errors = False
   gp.factor_shard = FactorShard() if mode == 'sharded' else None
   a, b, c = shard_coef(1.0, 10. * B * world, B * world, world, factor_sharded=mode == 'sharded')
