@@ -232,8 +232,85 @@ def run_reference_retrain(kw, dtype):
     torch.set_default_dtype(old)
 
 
+# DeepRBFKernel (var_gp/kernels.py:80-96): name -> shapes; fixtures dkl_*.pt also carry the MLP weights
+DKL_CASES = {
+  'dkl_t1': dict(C=4, Din=20, Fd=16, M=9, t=1, B=48, H=2, F=5, seed=51),
+  'dkl_t0': dict(C=3, Din=12, Fd=8, M=5, t=0, B=17, H=3, F=2, seed=52),
+}
+
+
+def dkl_case(kw, dtype):
+  """Seeded DKL problem: hypers / variational parameters / noise from make_case at the FEATURE dimension, inputs and
+  inducing inputs at the input dimension, MLP weights from torch.manual_seed(seed)."""
+  import torch.nn as nn
+  from vargp_b200.synthetic import make_case
+  C, Din, Fd, M, t, B, H, F, seed = (kw[k] for k in ('C', 'Din', 'Fd', 'M', 't', 'B', 'H', 'F', 'seed'))
+  params, prev, _, y, noise = make_case(C=C, D=Fd, M=M, t=t, B=B, H=H, F=F, sigma=1.5, seed=seed, dtype=dtype)
+  g = torch.Generator().manual_seed(seed + 7)
+  U = lambda *sh: torch.rand(*sh, generator=g, dtype=torch.float64).to(dtype)
+  params = dict(params, z=U(C, M, Din))
+  x = U(B, Din)
+  prev = [dict(p, z=U(C, M, Din)) for p in prev]
+  old = torch.get_default_dtype()
+  torch.set_default_dtype(torch.float32)       # nn.Linear's init consumes the generator in a dtype-dependent way:
+  try:                                         # always draw the weights in fp32 and cast
+    torch.manual_seed(seed)
+    phi = nn.Sequential(nn.Linear(Din, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, Fd))
+  finally:
+    torch.set_default_dtype(old)
+  return params, prev, x, y, noise, {k: v.detach().to(dtype) for k, v in phi.state_dict().items()}
+
+
+def build_dkl_model(VARGP, DeepRBFKernel, MulticlassSoftmax, kw, params, prev, phi_sd, dtype):
+  kern = DeepRBFKernel(kw['Din'], feature_size=kw['Fd'], prior_log_mean=params['prior_log_mean'].clone(),
+                       prior_log_logvar=params['prior_log_logvar'].clone())
+  gp = VARGP(params['z'].clone(), kern, MulticlassSoftmax(n_f=kw['F']), n_var_samples=kw['H'],
+             prev_params=[{k: v.clone() for k, v in p.items()} for p in prev]).to(dtype)
+  gp.kernel.phi.load_state_dict(phi_sd)
+  with torch.no_grad():
+    gp.u_mean.copy_(params['u_mean']); gp.u_tril_vec.copy_(params['u_tril_vec'])
+    gp.kernel.log_mean.copy_(params['log_mean']); gp.kernel.log_logvar.copy_(params['log_logvar'])
+  return gp
+
+
+def run_reference_dkl(kw, dtype):
+  from var_gp.vargp import VARGP
+  from var_gp.kernels import DeepRBFKernel
+  from var_gp.likelihoods import MulticlassSoftmax
+  old = torch.get_default_dtype()
+  torch.set_default_dtype(dtype)
+  try:
+    params, prev, x, y, noise, phi_sd = dkl_case(kw, dtype)
+    gp = build_dkl_model(VARGP, DeepRBFKernel, MulticlassSoftmax, kw, params, prev, phi_sd, dtype)
+    draws = [noise['eps_theta']] + ([noise['eps_u']] if prev else []) + [noise['eps_f']]
+    with pinned_noise(draws):
+      kl_h, kl_u, nll = gp.loss(x, y)
+    beta, Ntot = 1.7, 10 * x.size(0)
+    total = beta * kl_h + kl_u + (Ntot / x.size(0)) * nll
+    gp.zero_grad()
+    total.backward()
+    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in gp.named_parameters()}
+    with torch.no_grad(), pinned_noise([noise['eps_theta'], noise['eps_f']]):
+      probs = gp.predict(x)
+    return dict(kl_hypers=kl_h.detach(), kl_u=kl_u.detach(), nll=nll.detach(), total=total.detach(), probs=probs,
+                beta=beta, Ntot=Ntot, grads=grads)
+  finally:
+    torch.set_default_dtype(old)
+
+
 def main():
   refmods = load_reference()
+  for name, kw in DKL_CASES.items():
+    rec = dict(case=kw, torch=torch.__version__)
+    for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
+      rec[tag] = run_reference_dkl(kw, dtype)
+    rec['phi'] = dkl_case(kw, torch.float32)[5]
+    path = os.path.join(HERE, name + '.pt')
+    torch.save(rec, path)
+    print(f'{name:24s} kl_u={rec["f64"]["kl_u"].item():.6f} nll={rec["f64"]["nll"].item():.6f} '
+          f'-> {os.path.getsize(path) / 1024:.0f} KiB')
+  if os.environ.get('VARGP_GOLDEN_ONLY') == 'dkl':
+    return
   for name, kw in RETRAIN_CASES.items():
     rec = dict(case=kw, torch=torch.__version__)
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):
