@@ -149,6 +149,47 @@ def sweep_dkl(n, rng):
         f'worst abs. error probs {worst["probs"]:.1e}')
 
 
+def sweep_utils(n, rng):
+  """var_gp/train_utils.py (EarlyStopper, compute_bwt, compute_accuracy, compute_acc_ent) of the live reference --
+  imported with inert stand-ins for its absent logging / optimizer dependencies (torch_optimizer, wandb) -- against
+  vargp_b200.train on random score sequences, accuracy matrices and a fixed classifier."""
+  import types
+  for mod in ('torch_optimizer', 'wandb'):
+    sys.modules.setdefault(mod, types.ModuleType(mod))
+  import var_gp.train_utils as ref
+  from torch.utils.data import TensorDataset
+  from vargp_b200 import train as new
+
+  class FixedClf:                                    # predict() = softmax of a fixed linear map: deterministic on both sides
+    def __init__(self, D, C, g):
+      self.Wm = torch.randn(D, C, generator=g)
+      self.z = torch.zeros(1)
+    def predict(self, x, noise=None):
+      return torch.softmax(x @ self.Wm, dim=-1)
+
+  for i in range(n):
+    patience, delta = rng.choice([-1, 0, 1, 3, 10]), rng.choice([1e-4, 1e-2, 0.0])
+    a, b = ref.EarlyStopper(patience=patience, delta=delta), new.EarlyStopper(patience=patience, delta=delta)
+    for step in range(rng.randrange(1, 30)):
+      if a.is_done():
+        break
+      score = round(rng.random(), rng.choice([1, 2, 6]))
+      a(score, step); b(score, step)
+      assert a.is_done() == b.is_done() and a.info() == b.info(), (i, step)
+    T = rng.randrange(1, 7)
+    acc = torch.rand(T, T, generator=torch.Generator().manual_seed(i))
+    ra, rb = ref.compute_bwt(acc), new.compute_bwt(acc)
+    assert (torch.isnan(ra) and torch.isnan(rb)) or torch.equal(ra, rb), (i, ra, rb)
+    g = torch.Generator().manual_seed(1000 + i)
+    N, D, C, bs = rng.randrange(1, 300), rng.randrange(1, 9), rng.randrange(2, 6), rng.choice([1, 7, 64, 512])
+    x, y = torch.randn(N, D, generator=g), torch.randint(0, C, (N,), generator=g)
+    clf = FixedClf(D, C, g)
+    assert ref.compute_accuracy(TensorDataset(x, y), clf, batch_size=bs) == new.compute_accuracy(new.TensorTask(x, y), clf, batch_size=bs)
+    (a1, e1), (a2, e2) = ref.compute_acc_ent(TensorDataset(x, y), clf, batch_size=bs), new.compute_acc_ent(new.TensorTask(x, y), clf, batch_size=bs)
+    assert a1 == a2 and abs(e1 - e2) <= 1e-5 * max(1.0, abs(e1)), (i, e1, e2)
+  print(f'utils sweep: {n} cases checked (EarlyStopper traces, compute_bwt, compute_accuracy, compute_acc_ent identical)')
+
+
 def main():
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
   rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -158,6 +199,8 @@ def main():
     return sweep_retrain(n, rng)
   if os.environ.get('VARGP_SWEEP') == 'dkl':
     return sweep_dkl(n, rng)
+  if os.environ.get('VARGP_SWEEP') == 'utils':
+    return sweep_utils(n, rng)
   worst = dict(terms=0.0, grads=0.0, probs=0.0)
   done = skipped = 0
   for i in range(n):
