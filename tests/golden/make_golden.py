@@ -298,8 +298,20 @@ def run_reference_dkl(kw, dtype):
     torch.set_default_dtype(old)
 
 
+def save_toy_data():
+  """ToyDataset of the live reference (var_gp/datasets.py:11-51) under a fixed seed -> data_toy_seed3.pt."""
+  from var_gp.datasets import ToyDataset
+  torch.manual_seed(3)
+  ds = ToyDataset(N_K=50)
+  torch.save(dict(seed=3, N_K=50, data=ds.data.clone(), targets=ds.targets.clone()), os.path.join(HERE, 'data_toy_seed3.pt'))
+  print('data_toy_seed3.pt', tuple(ds.data.shape))
+
+
 def main():
   refmods = load_reference()
+  save_toy_data()
+  if os.environ.get('VARGP_GOLDEN_ONLY') == 'toydata':
+    return
   for name, kw in DKL_CASES.items():
     rec = dict(case=kw, torch=torch.__version__)
     for dtype, tag in ((torch.float32, 'f32'), (torch.float64, 'f64')):

@@ -190,6 +190,54 @@ def sweep_utils(n, rng):
   print(f'utils sweep: {n} cases checked (EarlyStopper traces, compute_bwt, compute_accuracy, compute_acc_ent identical)')
 
 
+def sweep_init(n, rng):
+  """Construction parity under the same seed: toy data (var_gp/datasets.py:21-51 vs synthetic.toy_data), and
+  create_clf of VARGP (plain / with prev_params / dkl) and VARGPRetrain -- inducing points picked by the same randperm
+  draws, same initial parameters, same hyper-prior hand-off: state dicts must be equal bit for bit."""
+  from var_gp.datasets import ToyDataset
+  from var_gp.vargp import VARGP as RefVARGP
+  from var_gp.vargp_retrain import VARGPRetrain as RefRetrain
+  from vargp_b200.vargp import VARGP
+  from vargp_b200.vargp_retrain import VARGPRetrain
+  from vargp_b200.synthetic import toy_data
+  from vargp_b200.train import TensorTask
+
+  def same(a, b, what):
+    assert list(a.keys()) == list(b.keys()), (what, list(a.keys()), list(b.keys()))
+    for k in a:
+      assert torch.equal(a[k], b[k]), (what, k)
+
+  for i in range(n):
+    seed = rng.randrange(10 ** 6)
+    N_K = rng.choice([5, 20, 50])
+    torch.manual_seed(seed); ds = ToyDataset(N_K=N_K)
+    torch.manual_seed(seed); X, Y = toy_data(N_K=N_K)
+    assert torch.equal(ds.data, X) and torch.equal(ds.targets, Y), i
+    M, n_f, n_v = rng.choice([3, 8, 20]), rng.choice([2, 10]), rng.choice([1, 3])
+    dkl, map_est, ep = rng.random() < 0.3, rng.random() < 0.3, rng.random() < 0.7
+    ds.filter_by_class([0, 1])
+    task = TensorTask.for_classes(X, Y, (0, 1))
+    kw = dict(M=M, n_f=n_f, n_var_samples=n_v, ep_var_mean=ep, map_est_hypers=map_est, dkl=dkl)
+    torch.manual_seed(seed + 1); a = RefVARGP.create_clf(ds, **kw)
+    torch.manual_seed(seed + 1); b = VARGP.create_clf(task, **kw)
+    same(a.state_dict(), b.state_dict(), 'task 0')
+    # second task: the previous state dict is handed over (the reference pops its kernel.* keys: give it a copy)
+    sd = {k: v.clone() + 0.01 for k, v in a.state_dict().items()}
+    ds.filter_by_class([2, 3])
+    task = TensorTask.for_classes(X, Y, (2, 3))
+    torch.manual_seed(seed + 2); a = RefVARGP.create_clf(ds, prev_params=[dict(sd)], **kw)
+    torch.manual_seed(seed + 2); b = VARGP.create_clf(task, prev_params=[dict(sd)], **kw)
+    same(a.state_dict(), b.state_dict(), 'task 1')
+    pa, pb = a.prev_params, b.prev_params
+    assert len(pa) == len(pb) == 1 and torch.equal(pa[0]['z'], pb[0]['z']) and torch.equal(pa[0]['u_mean'], pb[0]['u_mean'])
+    if not dkl:
+      rkw = dict(M=M, n_f=n_f, n_var_samples=n_v)
+      torch.manual_seed(seed + 3); a = RefRetrain.create_clf(ds, prev_params=[dict(sd)], **rkw)
+      torch.manual_seed(seed + 3); b = VARGPRetrain.create_clf(task, prev_params=[dict(sd)], **rkw)
+      same(a.state_dict(), b.state_dict(), 'retrain')
+  print(f'init sweep: {n} cases checked (toy data, create_clf state dicts of VARGP / dkl / prev_params / VARGPRetrain bit-identical)')
+
+
 def main():
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
   rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -201,6 +249,8 @@ def main():
     return sweep_dkl(n, rng)
   if os.environ.get('VARGP_SWEEP') == 'utils':
     return sweep_utils(n, rng)
+  if os.environ.get('VARGP_SWEEP') == 'init':
+    return sweep_init(n, rng)
   worst = dict(terms=0.0, grads=0.0, probs=0.0)
   done = skipped = 0
   for i in range(n):

@@ -39,3 +39,18 @@ def test_shard_loss_coefficients_sum_to_full_batch_loss():
   parts = sum(shard_loss(kl_h, kl_u, n, 1.7, 240., 24, 2) for n in nll_r)
   assert torch.isclose(parts, full)
   assert shard_coef(1.7, 240., 24, 2) == (0.85, 0.5, 10.0)
+
+
+def test_toy_data_reproduces_the_reference_dataset():
+  """synthetic.toy_data issues the reference ToyDataset's draws (var_gp/datasets.py:21-51): same seed, same data
+  (fixture recorded from the live reference by tests/golden/make_golden.py)."""
+  import os
+  from tests import util
+  from vargp_b200.synthetic import toy_data
+  rec = torch.load(os.path.join(util.GOLDEN_DIR, 'data_toy_seed3.pt'))
+  torch.manual_seed(rec['seed'])
+  X, Y = toy_data(N_K=rec['N_K'])
+  assert torch.equal(Y, rec['targets'])
+  assert (X - rec['data']).abs().max().item() < 1e-6      # same draws; allow for BLAS rounding of the 2 x 2 transform
+  task = TensorTask.for_classes(X, Y, (0, 1))
+  assert len(task) == 2 * rec['N_K'] and torch.unique(task.targets).numel() == 4

@@ -12,7 +12,7 @@ GRAD_KEYS = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
 
 def golden_names():
   """VARGP fixtures (make_golden.CASES)."""
-  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith(('retrain_', 'dkl_')))
+  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith(('retrain_', 'dkl_', 'data_')))
 
 
 def retrain_names():

@@ -49,3 +49,24 @@ def make_retrain_case(C, D, M, t, B, H=3, F=10, seed=0, sigma=10., dtype=torch.f
     noise['eps_q'] = Nrm(H, H, C, (t + 1) * M).to(dtype)
     noise['eps_p'] = Nrm(H, H, H, C, t * M).to(dtype)
   return params, retrain, prev, x, y, noise
+
+
+def toy_data(N_K=50, K=4):
+  """The reference's 4-class 2-D toy problem (var_gp/datasets.py:21-51, BASELINE configs[0]): issues the same global-RNG
+  draws in the same order (six randn columns, then a 2-D Gaussian for class 3), so under the same torch.manual_seed it
+  returns the same (X (4 N_K, 2), Y (4 N_K,)) as ToyDataset()._init_data.  Feed it to train.TensorTask."""
+  col = lambda m, s: m + s * torch.randn(N_K, 1)
+  X1 = torch.cat([col(0.8, 0.4), col(1.5, 0.4)], dim=-1)
+  X2 = torch.cat([col(0.5, 0.6), col(-0.2, -0.1)], dim=-1)
+  X3 = torch.cat([col(2.5, -0.1), col(1.0, 0.6)], dim=-1)
+  # MultivariateNormal(mean, covariance_matrix=S).sample([N_K]) = mean + eps L^T, eps ~ N(0, I) of shape (N_K, 2)
+  L = torch.linalg.cholesky(torch.tensor([[0.2, 0.1], [0.1, 0.1]]))
+  # (the draw goes through the same helper as MultivariateNormal.rsample: on CPU it is not the randn stream)
+  from torch.distributions.utils import _standard_normal
+  eps = _standard_normal(torch.Size([N_K, 2]), dtype=L.dtype, device=L.device)
+  X4 = torch.tensor([-0.5, 1.5]) + (L @ eps.unsqueeze(-1)).squeeze(-1)
+  X = torch.cat([X1, X2, X3, X4], dim=0)
+  X[:, 1] -= 1
+  X[:, 0] -= 0.5
+  Y = torch.arange(4).repeat_interleave(N_K)
+  return X, Y
