@@ -375,6 +375,16 @@ def run_gpu(args):
                         gbs=round(v['bytes'] / max(v['ms'], 1e-9) / 1e6, 1)) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms'])},
     'kernel_ms_per_step': round(total_kernel_ms, 4),
   }
+  try:
+    # per-kernel share of its own roofline (tensor kernels against the 3xTF32 peak, everything else against the
+    # measured HBM copy bandwidth); latency-sized kernels of this small workload show up as a few per cent
+    tf_peak = pk['bf16_sustained'] / 6.0
+    for k, v in line['kernels'].items():
+      tensor = k.startswith('gemm_tc') or k == 'chol_inv'
+      v['bound'] = 'tensor' if tensor else 'hbm'
+      v['frac'] = round(v['tflops'] / tf_peak, 4) if tensor else round(v['gbs'] / pk['hbm'], 4)
+  except Exception as e:            # never lose the bench line over a reporting extra
+    line['kernels_note'] = f'per-kernel roofline fractions unavailable: {type(e).__name__}'
   if cpu is not None:
     line['cpu_baseline'] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in cpu.items()}
   if args.detail:
