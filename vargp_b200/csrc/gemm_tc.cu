@@ -402,6 +402,7 @@ using namespace vargp;
 // small-shape variant (128 x 64 tiles, two CTAs per SM): used when the 128 x 128 grid would have at most this many CTAs
 static int64_t g_tcs_max_ctas = -1;            // < 0: off (default)
 static int64_t g_tcs_launches = 0;
+static bool g_tcs_ok = false;
 
 int vargp_tc_init() {
   if (g_tc_ready) return 0;
@@ -412,10 +413,12 @@ int vargp_tc_init() {
   g_encode = (EncodeTiledFn)fn;
   e = cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64, 2>::SMEM_BYTES);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return (int)e;
+  // the opt-in small-shape variant must never take the default path down: if its attributes cannot be set it stays off
+  g_tcs_ok = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<64, 2>::SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+  if (!g_tcs_ok) cudaGetLastError();
   const char* env = getenv("VARGP_TCS_MAX_CTAS");
   if (env) g_tcs_max_ctas = atoll(env);
   int rc = tc2_init();
@@ -461,7 +464,7 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
 
   const int64_t ctas128 = ceil_div(g->N, 128) * ceil_div(g->M, TC_BM) * nbatch;
   const bool big = tc2_wants(g);
-  const bool small = !big && g_tcs_max_ctas >= 0 && ctas128 <= g_tcs_max_ctas;
+  const bool small = !big && g_tcs_ok && g_tcs_max_ctas >= 0 && ctas128 <= g_tcs_max_ctas;
 
   alignas(64) CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->M, g->K, g->a_rs, g->a_cs, g->nb, g->a_bs, p.a_mn, p.a_b);
