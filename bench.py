@@ -2,7 +2,7 @@
 """ELBO training-step benchmark for the VAR-GP hot path (contract: task prompt section 4 + base contract).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--task T] [--workload split_mnist|permuted_mnist|scaled]
-    python bench.py --impl reference ...      # the reference algorithm (CPU oracle port) on the host cores
+    python bench.py --impl reference ...      # the unmodified reference (oracle/_ref) on the host cores
 
 One "step" mirrors experiments/vargp.py:30-37 of the reference:
     zero_grad -> kl_h, kl_u, lik = gp.loss(x, y) -> loss = beta*kl_h + kl_u + (N/B)*lik -> backward -> Yogi step.
@@ -13,7 +13,8 @@ inducing points per class), synthetic data, learned-lengthscale regime (SURVEY.m
 Prints ONE JSON line (rank 0).  `value` = minibatch ELBO steps per second with inputs resident in HBM,
 aggregated over ranks (weak scaling: every rank steps its own 512-point minibatch, gradients all-reduced);
 `e2e` = the same through the public API from pinned HOST buffers (H2D of x, y and D2H of the three loss
-terms inside the timed region).
+terms inside the timed region).  The default line also carries `scaled`: the scaled synthetic config (B=65536
+sharded over the ranks, P=2048; strong scaling) measured in the same run.
 """
 import argparse
 import json
@@ -71,7 +72,7 @@ def measure_tf32_cublas(dev, n=8192, reps=5):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+  """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
   Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -81,7 +82,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                    '--format=csv,noheader,nounits', '-lms', '200'],
+                                    '--format=csv,noheader,nounits', '-lms', '50'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.th = threading.Thread(target=self._read, daemon=True)
       self.th.start()
@@ -154,30 +155,82 @@ def synth_batches(n, B, D, C, task, device, seed, pin=False):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference algorithm (oracle port, op for op) on the host cores
+# shared description of the workload (both arms print the SAME config dict)
+# ------------------------------------------------------------------------------------------------
+def factor_sharded(wl, task, world, no_shard=False):
+  """ElboStepper's default rule: shard the O(P^3) factor stage over the ranks when P >= 512."""
+  return (not no_shard) and world > 1 and (task + 1) * WORKLOADS[wl]['M'] >= 512
+
+
+def pool_batches(B, D):
+  """minibatch pool larger than the 126 MB L2, rotated every step"""
+  return max(4, math.ceil(260e6 / (B * D * 4)))
+
+
+def bench_config(wl, task, world, batch=None, no_shard=False):
+  cfg = WORKLOADS[wl]
+  gB = batch or cfg['B']
+  B = gB // world if wl == 'scaled' else gB
+  per = f'B={B} per rank' if wl != 'scaled' else f'B={gB} global ({B} per rank)'
+  sharded = factor_sharded(wl, task, world, no_shard)
+  return {
+    'workload': f'{wl} shape, task t={task}: C={cfg["C"]}, D={cfg["D"]}, M={cfg["M"]}/task, P={(task + 1) * cfg["M"]}, '
+                f'{per}, H={H}, F={F}, beta={cfg["beta"]}, Yogi',
+    'l2': f'inputs rotate over a {pool_batches(B, cfg["D"]) * B * cfg["D"] * 4 / 1e6:.0f} MB minibatch pool (> 126 MB L2)',
+    'parallelism': (f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL ' +
+                    ('sharded over (h,c) pairs (all-gather W,N,nu; reduce-scatter Wbar,G,nubar)' if sharded else 'replicated') +
+                    ', 1 NCCL gradient all-reduce/step'),
+  }
+
+
+METRIC = {False: 'ELBO training steps/s (512-point minibatch steps, summed over ranks)',
+          True: 'ELBO training steps/s (global minibatch sharded over ranks)'}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_steps(wl, task, steps, warmup, budget_s, threads=None):
-  from oracle import vargp_oracle as orc
+  """Full ELBO training steps (experiments/vargp.py:30-37: zero_grad, loss, backward, Yogi step) on the host cores.
+  kind = "reference": the UNMODIFIED reference modules copied to oracle/_ref by oracle/make_ref.py, stock code path
+  (its own RNG draws, torch.distributions objects, the B x B Gram ...); kind = "port": the oracle restatement, when
+  oracle/_ref is absent.  Both share the Yogi of vargp_b200.optim (torch_optimizer is not in the image)."""
   from vargp_b200.optim import Yogi
+  from oracle import ref_runner
   threads = threads or os.cpu_count()
   torch.set_num_threads(threads)
   cfg, params, prev = make_problem(wl, task, 'cpu')
-  leaf_keys = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
-  p = {k: (v.clone().requires_grad_(True) if k in leaf_keys else v) for k, v in params.items()}
-  opt = Yogi([p[k] for k in leaf_keys], lr=3e-3)
   B, D, C = cfg['B'], cfg['D'], cfg['C']
   xs, ys = synth_batches(4, B, D, C, task, 'cpu', seed=7)
   Q = task * cfg['M']
+  if ref_runner.available() and os.environ.get('VARGP_BENCH_PORT', '0') == '0':
+    kind = 'reference'
+    gp = ref_runner.build_model(params, prev, H, F)
+    opt = Yogi(gp.parameters(), lr=3e-3)
+    torch.manual_seed(4321)
 
-  def one(i):
-    opt.zero_grad(set_to_none=True)
-    noise = dict(eps_theta=torch.randn(H, D + 1), eps_f=torch.randn(H, F, C, B))
-    if task > 0:
-      noise['eps_u'] = torch.randn(H, H, C, Q)
-    kl_h, kl_u, nll = orc.elbo_terms(p, prev, xs[i % 4], ys[i % 4], noise, n_v=H)
-    loss = cfg['beta'] * kl_h + kl_u + (cfg['N'] / B) * nll
-    loss.backward()
-    opt.step()
+    def one(i):
+      opt.zero_grad(set_to_none=True)
+      kl_h, kl_u, nll = gp.loss(xs[i % 4], ys[i % 4])
+      loss = cfg['beta'] * kl_h + kl_u + (cfg['N'] / B) * nll
+      loss.backward()
+      opt.step()
+  else:
+    kind = 'port'
+    from oracle import vargp_oracle as orc
+    leaf_keys = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
+    p = {k: (v.clone().requires_grad_(True) if k in leaf_keys else v) for k, v in params.items()}
+    opt = Yogi([p[k] for k in leaf_keys], lr=3e-3)
+
+    def one(i):
+      opt.zero_grad(set_to_none=True)
+      noise = dict(eps_theta=torch.randn(H, D + 1), eps_f=torch.randn(H, F, C, B))
+      if task > 0:
+        noise['eps_u'] = torch.randn(H, H, C, Q)
+      kl_h, kl_u, nll = orc.elbo_terms(p, prev, xs[i % 4], ys[i % 4], noise, n_v=H)
+      loss = cfg['beta'] * kl_h + kl_u + (cfg['N'] / B) * nll
+      loss.backward()
+      opt.step()
 
   t0 = time.perf_counter()
   one(0)
@@ -191,125 +244,225 @@ def cpu_reference_steps(wl, task, steps, warmup, budget_s, threads=None):
   for i in range(steps_eff):
     one(i)
   dt = time.perf_counter() - t1
-  return dict(steps=steps_eff, ms_per_step=1e3 * dt / steps_eff, value=steps_eff / dt, cores=threads)
+  what = ('the unmodified reference modules (oracle/_ref, stock code path incl. its BxB Gram)' if kind == 'reference'
+          else 'the oracle port of the reference algorithm (reference op order incl. its BxB Gram)')
+  return dict(steps=steps_eff, ms_per_step=1e3 * dt / steps_eff, value=steps_eff / dt, cores=threads, kind=kind,
+              sample=f'{steps_eff} full ELBO steps (fwd+bwd+Yogi) of the same workload on {what}, fp32, {threads} host threads')
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_gpu(args):
-  import torch.distributed as dist
-  import datetime
-  rank = int(os.environ.get('RANK', 0))
-  t_start = time.time()
+class Ctx:
+  """Process-wide state of one bench run (rank / world / device, barrier + max-over-ranks timing)."""
 
-  def log(msg):
-    if args.verbose:
-      print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}', file=sys.stderr, flush=True)
-  world = int(os.environ.get('WORLD_SIZE', 1))
-  local = int(os.environ.get('LOCAL_RANK', 0))
-  torch.cuda.set_device(local)
-  dev = torch.device('cuda', local)
-  if world > 1:
-    dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=120))
-    log('process group up')
-  from vargp_b200 import ops as vops
-  wl, task = args.workload, args.task
-  cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
-  gp = build_gpu_model(params, prev, dev)
-  ops = vops.get_ops()
-  if args.batch:
-    cfg = dict(cfg, B=args.batch)
-  B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
-  global_B = B * world
-  # scaled: ~100 GB of workspaces live once in the eager allocator; a graph-private pool on top of the warm-up pool
-  # would not fit.  N > 1: the graph covers zero_grad .. backward, the all-reduce and the Yogi step follow eagerly.
-  use_graph = (not args.no_graph) and wl != 'scaled'
-  from vargp_b200.train import ElboStepper
-  stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
-                        use_graph=use_graph, shard_factor=False if args.no_shard_factor else None)
-  # minibatch pool larger than the 126 MB L2, rotated every step
-  n_pool = max(4, math.ceil(260e6 / (B * D * 4)))
-  xs, ys = synth_batches(n_pool, B, D, C, task, dev, seed=rank)
-  torch.manual_seed(1234)                               # identical theta draws on every rank
+  def __init__(self, args):
+    import torch.distributed as dist
+    import datetime
+    self.args, self.dist = args, dist
+    self.rank = int(os.environ.get('RANK', 0))
+    self.world = int(os.environ.get('WORLD_SIZE', 1))
+    self.local = int(os.environ.get('LOCAL_RANK', 0))
+    self.t_start = time.time()
+    torch.cuda.set_device(self.local)
+    self.dev = torch.device('cuda', self.local)
+    if self.world > 1:
+      dist.init_process_group('nccl', device_id=self.dev, timeout=datetime.timedelta(seconds=180))
+      self.log('process group up')
 
-  def step(x, y):
-    return stepper.step(x, y)
+  def log(self, msg):
+    if self.args.verbose:
+      print(f'[bench rank {self.rank} +{time.time() - self.t_start:6.1f}s] {msg}', file=sys.stderr, flush=True)
 
-  def barrier():
-    if world > 1:
-      dist.barrier()
+  def barrier(self):
+    if self.world > 1:
+      self.dist.barrier()
     torch.cuda.synchronize()
 
-  def timed(fn, steps):
+  def timed(self, fn, steps):
+    """EXACTLY `steps` calls between barrier + synchronize on both sides, CUDA events, MAX over ranks -> ms."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    self.barrier()
     e0.record()
     for i in range(steps):
       fn(i)
     e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    self.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+    if self.world > 1:
+      self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
     return float(ms)
 
-  K, Wm = args.steps, max(3, args.warmup)
-  sampler = ClockSampler(local)
+
+def run_workload(ctx, wl, task, K, Wm, want_e2e=True, batch=None):
+  """Warm up, time K steps (device-resident inputs), time K end-to-end steps (pinned host inputs), then one serialised
+  instrumented pass for the per-kernel table.  Returns a dict of raw measurements (rank 0 assembles the JSON)."""
+  from vargp_b200 import ops as vops
+  from vargp_b200 import elbo
+  from vargp_b200.train import ElboStepper
+  args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
+  cfg, params, prev = make_problem(wl, task, dev)       # same seed on every rank: replicated parameters
+  gp = build_gpu_model(params, prev, dev)
+  del params, prev
+  ops = vops.get_ops()
+  if batch:
+    cfg = dict(cfg, B=batch)
+  B, D, C = cfg['B'] // (world if wl == 'scaled' else 1), cfg['D'], cfg['C']
+  # scaled: ~100 GB of workspaces live once in the eager allocator; a graph-private pool on top of the warm-up pool
+  # would not fit, and at 50..400 ms per step launch overhead is irrelevant.
+  use_graph = (not args.no_graph) and wl != 'scaled'
+  stepper = ElboStepper(gp, n_data=cfg['N'], batch_size=B, beta=cfg['beta'], lr=3e-3, world_size=world,
+                        use_graph=use_graph, shard_factor=False if args.no_shard_factor else None)
+  n_pool = pool_batches(B, D)
+  xs, ys = synth_batches(n_pool, B, D, C, task, dev, seed=rank)
+  torch.manual_seed(1234)                               # identical theta draws on every rank
+
+  def step(i):
+    return stepper.step(xs[i % n_pool], ys[i % n_pool])
+
+  sampler = ClockSampler(ctx.local)
   if rank == 0:
     sampler.start()
   for i in range(Wm):
-    step(xs[i % n_pool], ys[i % n_pool])
-  gp.check_errors()
+    step(i)
+  stepper.check_errors()
   if rank == 0:
     sampler.wait_first()
-  # keep the GPUs under load until the sampler is live, then mark the start of the timed region
-  for i in range(Wm):
-    step(xs[i % n_pool], ys[i % n_pool])
+  for i in range(Wm):      # keep the GPUs under load until the sampler is live, then mark the start of the timed region
+    step(i)
+  ctx.barrier()
   if rank == 0:
     sampler.mark()
   l0 = ops.launch_count()
-  ms = timed(lambda i: step(xs[i % n_pool], ys[i % n_pool]), K)
+  ms = ctx.timed(step, K)
   launches = ops.launch_count() - l0
-  if use_graph:
+  if stepper.use_graph:
     launches = stepper.launches_per_step * K          # replayed from the captured CUDA graph
   clocks = sampler.stop() if rank == 0 else None
-  gp.check_errors()
-  log(f'timed region done: {ms / K:.3f} ms/step')
+  stepper.check_errors()
+  ctx.log(f'{wl}: timed region done: {ms / K:.3f} ms/step')
+  out = dict(wl=wl, task=task, K=K, Wm=Wm, ms=ms, launches=int(launches), clocks=clocks, B=B, cfg=cfg,
+             use_graph=bool(stepper.use_graph), tail_in_graph=bool(getattr(stepper, '_tail_in_graph', world == 1)),
+             sharded=stepper.shard is not None, ms_e2e=None)
 
   # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the three loss terms ----
-  xh, yh = synth_batches(8, B, D, C, task, dev, seed=100 + rank, pin=True)
-  out_h = torch.empty(3, pin_memory=True)
+  if want_e2e:
+    xh, yh = synth_batches(8, B, D, C, task, dev, seed=100 + rank, pin=True)
+    sink = torch.zeros(3)
 
-  def e2e_step(i):
-    # H2D from pinned host memory: this step's inputs were announced by the previous call (`prefetch`) and copied on
-    # the copy stream while that step ran; this call announces the next minibatch the same way.  Every timed step
-    # thus issues one minibatch H2D and one D2H of its own three loss terms inside the timed region.
-    stepper.step(xh[i % 8], yh[i % 8], prefetch=(xh[(i + 1) % 8], yh[(i + 1) % 8]))
-    out_h.copy_(stepper.terms_vec, non_blocking=False)                  # D2H of the loss terms (syncs)
+    def e2e_step(i):
+      # H2D from pinned host memory: this step's inputs were announced by the previous call (`prefetch`) and copied on
+      # the copy stream while that step ran; this call announces the next minibatch the same way.  D2H: the step's
+      # three loss terms go to a pinned ring without stalling the launch of the next step; the host reads them one
+      # step late (the timed region ends with a synchronize, so every step's D2H completes inside it).
+      stepper.step(xh[i % 8], yh[i % 8], prefetch=(xh[(i + 1) % 8], yh[(i + 1) % 8]))
+      stepper.fetch_terms_async()
+      t = stepper.host_terms(lag=1)
+      if t is not None:
+        sink.add_(t)
 
-  for i in range(3):
-    e2e_step(i)
-  ms_e2e = timed(e2e_step, K)
-  log(f'e2e done: {ms_e2e / K:.3f} ms/step')
+    for i in range(3):
+      e2e_step(i)
+    out['ms_e2e'] = ctx.timed(e2e_step, K)
+    if not bool(torch.isfinite(sink).all()):
+      raise RuntimeError('non-finite loss terms in the end-to-end loop')
+    ctx.log(f'{wl}: e2e done: {out["ms_e2e"] / K:.3f} ms/step')
+    del xh, yh
 
-  # ---- per-kernel device times (separate instrumented pass, never inside a timed region) ----
-  # (every rank runs it: the step contains the gradient all-reduce; only rank 0's record is reported)
-  stepper.use_graph = False                           # eager launches so that each one can be bracketed by events
+  # ---- per-kernel device times: separate SERIALISED pass (no side stream, no programmatic dependent launch, eager
+  #      launches each bracketed by CUDA events), never inside a timed region.  Every rank runs it (the step contains
+  #      collectives); only rank 0's record is reported. ----
+  stepper.use_graph = False
+  side, elbo.USE_SIDE_STREAM = elbo.USE_SIDE_STREAM, False
+  pdl = ops.set_pdl(False)
+  step(0)                                              # warm the eager allocator pool of this schedule
   ops.profile_start()
   nprof = 3
   for i in range(nprof):
-    step(xs[i % n_pool], ys[i % n_pool])
+    step(i)
   prof = ops.profile_stop()
-  stepper.use_graph = use_graph
+  ops.set_pdl(pdl)
+  elbo.USE_SIDE_STREAM = side
   for d in prof.values():
     for k in ('ms', 'flops', 'bytes'):
       d[k] /= nprof
     d['calls'] //= nprof
-  log('instrumented pass done')
+  out['prof'] = prof
+  ctx.log(f'{wl}: instrumented pass done')
+  del stepper, gp, xs, ys
+  import gc
+  gc.collect()
+  torch.cuda.empty_cache()
+  return out
+
+
+def latest_traffic():
+  """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from the newest committed `ncu --set full`
+  summary profiles/r*_traffic.json -> {kernel: bytes}"""
+  import glob
+  paths = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))
+  if not paths:
+    return {}, None
+  d = json.load(open(paths[-1]))
+  return {k: v.get('bytes_per_launch') for k, v in d.items() if isinstance(v, dict)}, os.path.basename(paths[-1])
+
+
+def kernel_tables(prof, pk, tf32_cublas=None):
+  """prof {tag: dict(kernel, ms, flops, bytes, calls)} -> (roofline of the dominant kernel, per-kernel table, total ms)"""
+  traffic, tsrc = latest_traffic()
+  by_kernel = {}
+  for tag, d in prof.items():
+    k = by_kernel.setdefault(d['kernel'], dict(ms=0.0, flops=0.0, bytes=0.0, calls=0))
+    for f_ in ('ms', 'flops', 'bytes', 'calls'):
+      k[f_] += d[f_]
+  total = sum(k['ms'] for k in by_kernel.values())
+  top = max(by_kernel, key=lambda k: by_kernel[k]['ms'])
+  tk = by_kernel[top]
+  tf_peak = pk['bf16_sustained'] / 6.0           # TF32 dense = bf16/2; 3xTF32 issues 3 MMAs per product
+  if top.startswith('gemm') or top == 'chol_inv':
+    ach = tk['flops'] / (tk['ms'] * 1e-3) / 1e12
+    roof = dict(kernel=top, bound='tensor', achieved=round(ach, 3), peak=round(tf_peak, 1), unit='TFLOP/s',
+                frac=round(ach / tf_peak, 4), traffic=traffic.get(top), traffic_src=tsrc,
+                peak_note=f'3xTF32 = {pk["src"]} bf16 sustained / 6',
+                ms_per_step=round(tk['ms'], 4), launches_per_step=tk['calls'],
+                share_of_kernel_time=round(tk['ms'] / total, 3))
+    if tf32_cublas is not None:             # cross-check of the denominator: cuBLAS TF32 8192^3 measured in this run
+      roof['tf32_cublas_tflops'] = round(tf32_cublas, 1)
+      roof['peak_3xtf32_from_tf32_cublas'] = round(tf32_cublas / 3.0, 1)
+  else:
+    ach = tk['bytes'] / (tk['ms'] * 1e-3) / 1e9
+    roof = dict(kernel=top, bound='hbm', achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
+                frac=round(ach / pk['hbm'], 4), traffic=traffic.get(top), traffic_src=tsrc,
+                peak_note=f'{pk["src"]} copy bandwidth', ms_per_step=round(tk['ms'], 4), launches_per_step=tk['calls'],
+                share_of_kernel_time=round(tk['ms'] / total, 3))
+  table = {}
+  for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms']):
+    tensor = k.startswith('gemm_tc') or k == 'chol_inv'
+    tfl, gbs = v['flops'] / max(v['ms'], 1e-9) / 1e9, v['bytes'] / max(v['ms'], 1e-9) / 1e6
+    table[k] = dict(ms=round(v['ms'], 4), calls=v['calls'], tflops=round(tfl, 3), gbs=round(gbs, 1),
+                    bound='tensor' if tensor else 'hbm', frac=round(tfl / tf_peak, 4) if tensor else round(gbs / pk['hbm'], 4))
+  return roof, table, total
+
+
+def run_gpu(args):
+  ctx = Ctx(args)
+  rank, world, dev = ctx.rank, ctx.world, ctx.dev
+  wl, task = args.workload, args.task
+  K, Wm = args.steps, max(3, args.warmup)
+  main = run_workload(ctx, wl, task, K, Wm, want_e2e=True, batch=args.batch)
+
+  # The north star's strong-scaling target is quoted on the scaled synthetic config (B=65536, P=2048): the default
+  # line carries it as a sub-record measured in the same run, so that the driver's 1/2/4/8-GPU sweep records the curve.
+  scaled = None
+  if wl == 'split_mnist' and not args.no_scaled:
+    try:
+      scaled = run_workload(ctx, 'scaled', 0, max(8, min(K, 10)), 3, want_e2e=False)
+    except Exception as e:                       # never lose the headline over the sub-record
+      scaled = dict(error=f'{type(e).__name__}: {e}'[:300])
+      ctx.log(f'scaled sub-record failed: {scaled["error"]}')
 
   tf32_cublas = None
-  if rank == 0 and wl != 'scaled':          # (the scaled run holds ~100 GB of workspaces; the Split-shape line carries it)
+  if rank == 0:
     try:
       tf32_cublas = measure_tf32_cublas(dev)
     except RuntimeError:
@@ -317,80 +470,66 @@ def run_gpu(args):
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     r = cpu_reference_steps(wl if wl != 'scaled' else 'split_mnist', task, 8, 1, budget_s=25.0)
-    cpu = dict(value=r['value'], unit='steps/s', cores=r['cores'], kind='port',
-               sample=f'{r["steps"]} full ELBO steps (fwd+bwd+Yogi) of the same workload on the oracle port '
-                      f'(reference op order incl. its BxB Gram), fp32, {r["cores"]} threads')
+    cpu = dict(value=r['value'], unit='steps/s', cores=r['cores'], kind=r['kind'], sample=r['sample'])
   if world > 1:
-    dist.destroy_process_group()
+    ctx.dist.destroy_process_group()
   if rank != 0:
     return
 
   pk = peaks()
-  traffic = {}
-  tpath = os.path.join(ROOT, 'profiles', 'r1b_traffic.json')       # per-launch DRAM bytes from the committed ncu captures
-  if os.path.exists(tpath):
-    traffic = {k: v.get('bytes_per_launch') for k, v in json.load(open(tpath)).items() if isinstance(v, dict)}
-  by_kernel = {}
-  for tag, d in prof.items():
-    k = by_kernel.setdefault(d['kernel'], dict(ms=0.0, flops=0.0, bytes=0.0, calls=0))
-    for f_ in ('ms', 'flops', 'bytes', 'calls'):
-      k[f_] += d[f_]
-  total_kernel_ms = sum(k['ms'] for k in by_kernel.values())
-  top = max(by_kernel, key=lambda k: by_kernel[k]['ms'])
-  tk = by_kernel[top]
-  if top.startswith('gemm'):
-    tf32x3_peak = pk['bf16_sustained'] / 6.0     # TF32 dense = bf16/2; 3xTF32 issues 3 MMAs per product
-    ach = tk['flops'] / (tk['ms'] * 1e-3) / 1e12
-    roof = dict(kernel=top, bound='tensor', achieved=round(ach, 3), peak=round(tf32x3_peak, 1), unit='TFLOP/s',
-                frac=round(ach / tf32x3_peak, 4), traffic=traffic.get('gemm_tc2' if wl == 'scaled' else top),
-                peak_note=f'3xTF32 = {pk["src"]} bf16 sustained / 6', share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
-    if tf32_cublas is not None:             # cross-check of the denominator: cuBLAS TF32 8192^3 measured in this run
-      roof['tf32_cublas_tflops'] = round(tf32_cublas, 1)
-      roof['peak_3xtf32_from_tf32_cublas'] = round(tf32_cublas / 3.0, 1)
-  else:
-    ach = tk['bytes'] / (tk['ms'] * 1e-3) / 1e9
-    roof = dict(kernel=top, bound='hbm', achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
-                frac=round(ach / pk['hbm'], 4), traffic=traffic.get(top), peak_note=f'{pk["src"]} copy bandwidth',
-                share_of_kernel_time=round(tk['ms'] / total_kernel_ms, 3))
-  value = world * K / (ms * 1e-3)
-  e2e_v = world * K / (ms_e2e * 1e-3)
+  is_scaled = wl == 'scaled'
+  ms, ms_e2e, B, cfg = main['ms'], main['ms_e2e'], main['B'], main['cfg']
+  D = cfg['D']
+  roof, table, total_kernel_ms = kernel_tables(main['prof'], pk, tf32_cublas)
+  nrank = 1 if is_scaled else world          # scaled: one global-minibatch step per K; else every rank steps its own
   line = {
-    'metric': 'ELBO training steps/s (512-point minibatch steps, summed over ranks)' if wl != 'scaled'
-              else 'ELBO training steps/s (global minibatch sharded over ranks)',
-    'value': round(value if wl != 'scaled' else K / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': world, 'steps': K,
+    'metric': METRIC[is_scaled],
+    'value': round(nrank * K / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': world, 'steps': K,
     'warmup': Wm, 'ms_per_step': round(ms / K, 4), 'higher_is_better': True,
-    'scaling': 'weak' if wl != 'scaled' else 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-    'config': {'workload': f'{wl} shape, task t={task}: C={C}, D={D}, M={cfg["M"]}/task, P={(task + 1) * cfg["M"]}, '
-                           f'B={B}/rank, H={H}, F={F}, beta={cfg["beta"]}, Yogi',
-               'l2': f'inputs rotate over a {n_pool * B * D * 4 / 1e6:.0f} MB minibatch pool (> 126 MB L2)',
-               'parallelism': (f'dp{world}: minibatch term sharded, Kzz/Cholesky/KL ' + ('sharded over (h,c) pairs (all-gather W,N,nu; reduce-scatter Wbar,G,nubar)' if stepper.shard is not None else 'replicated') + ', 1 NCCL gradient all-reduce/step'),
-               'cuda_graph': bool(use_graph)},
-    'e2e': {'value': round(e2e_v if wl != 'scaled' else K / (ms_e2e * 1e-3), 3), 'unit': 'steps/s',
-            'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 12, 'ms_per_step': round(ms_e2e / K, 4)},
-    'gpu_launches': int(launches),
-    'clocks': clocks,
+    'scaling': 'strong' if is_scaled else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+    'config': bench_config(wl, task, world, args.batch, args.no_shard_factor),
+    'cuda_graph': main['use_graph'], 'collectives_in_graph': main['use_graph'] and main['tail_in_graph'] and world > 1,
+    'e2e': {'value': round(nrank * K / (ms_e2e * 1e-3), 3), 'unit': 'steps/s',
+            'h2d_bytes_per_step': B * D * 4 + B * 8, 'd2h_bytes_per_step': 12, 'ms_per_step': round(ms_e2e / K, 4),
+            'note': 'ElboStepper.step from pinned host minibatches (H2D prefetched on a copy stream beside the previous '
+                    'step) + D2H of the three loss terms per step, read by the host one step late'},
+    'gpu_launches': main['launches'],
+    'clocks': main['clocks'],
     'roofline': roof,
-    'kernels': {k: dict(ms=round(v['ms'], 4), calls=v['calls'],
-                        tflops=round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 3),
-                        gbs=round(v['bytes'] / max(v['ms'], 1e-9) / 1e6, 1)) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms'])},
+    'kernels': table,
     'kernel_ms_per_step': round(total_kernel_ms, 4),
+    'kernels_note': 'per-kernel times from a separate SERIALISED eager pass (no side stream, no PDL): their sum exceeds '
+                    'ms_per_step by what the step graph overlaps',
   }
-  try:
-    # per-kernel share of its own roofline (tensor kernels against the 3xTF32 peak, everything else against the
-    # measured HBM copy bandwidth); latency-sized kernels of this small workload show up as a few per cent
-    tf_peak = pk['bf16_sustained'] / 6.0
-    for k, v in line['kernels'].items():
-      tensor = k.startswith('gemm_tc') or k == 'chol_inv'
-      v['bound'] = 'tensor' if tensor else 'hbm'
-      v['frac'] = round(v['tflops'] / tf_peak, 4) if tensor else round(v['gbs'] / pk['hbm'], 4)
-  except Exception as e:            # never lose the bench line over a reporting extra
-    line['kernels_note'] = f'per-kernel roofline fractions unavailable: {type(e).__name__}'
+  if scaled is not None:
+    if 'error' in scaled:
+      line['scaled'] = scaled
+    else:
+      sroof, stable, stotal = kernel_tables(scaled['prof'], pk, tf32_cublas)
+      sK, sms, sc = scaled['K'], scaled['ms'], scaled['clocks'] or {}
+      rec = {
+        'metric': METRIC[True], 'value': round(sK / (sms * 1e-3), 4), 'unit': 'steps/s', 'scaling': 'strong',
+        'steps': sK, 'warmup': scaled['Wm'], 'ms_per_step': round(sms / sK, 3),
+        'config': bench_config('scaled', 0, world, None, args.no_shard_factor),
+        'clocks': scaled['clocks'], 'gpu_launches': scaled['launches'],
+        'roofline': sroof, 'kernels': stable, 'kernel_ms_per_step': round(stotal, 3),
+      }
+      if sc.get('sm_mhz') and sc.get('sm_max_mhz'):
+        # power-capped runs clock differently at different N: the same time rescaled to the max SM clock
+        rec['ms_per_step_at_max_clock'] = round(sms / sK * sc['sm_mhz'] / sc['sm_max_mhz'], 3)
+      line['scaled'] = rec
   if cpu is not None:
     line['cpu_baseline'] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in cpu.items()}
   if args.detail:
     line['call_sites'] = {t: dict(kernel=d['kernel'], ms=round(d['ms'], 4), calls=d['calls'],
-                                  tflops=round(d['flops'] / max(d['ms'], 1e-9) / 1e9, 3)) for t, d in
-                          sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+                                  tflops=round(d['flops'] / max(d['ms'], 1e-9) / 1e9, 3),
+                                  gbs=round(d['bytes'] / max(d['ms'], 1e-9) / 1e6, 1)) for t, d in
+                          sorted(main['prof'].items(), key=lambda kv: -kv[1]['ms'])}
+    if scaled is not None and 'prof' in scaled:
+      line['scaled']['call_sites'] = {t: dict(kernel=d['kernel'], ms=round(d['ms'], 4), calls=d['calls'],
+                                              tflops=round(d['flops'] / max(d['ms'], 1e-9) / 1e9, 3),
+                                              gbs=round(d['bytes'] / max(d['ms'], 1e-9) / 1e6, 1)) for t, d in
+                                      sorted(scaled['prof'].items(), key=lambda kv: -kv[1]['ms'])}
   print(json.dumps(line))
 
 
@@ -398,21 +537,18 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', 0))
   if rank != 0:
     return
-  cfg = WORKLOADS[args.workload]
+  world = int(os.environ.get('WORLD_SIZE', args.gpus))
   wl = args.workload if args.workload != 'scaled' else 'split_mnist'
   r = cpu_reference_steps(wl, args.task, args.steps, args.warmup, budget_s=170.0)
-  B, C, D = cfg['B'], cfg['C'], cfg['D']
   line = {
     'impl': 'reference',
-    'metric': 'ELBO training steps/s (512-point minibatch steps, summed over ranks)',
-    'value': round(r['value'], 4), 'unit': 'steps/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)),
+    'metric': METRIC[False],
+    'value': round(r['value'], 4), 'unit': 'steps/s', 'n_gpus': world,
     'steps': r['steps'], 'warmup': args.warmup, 'ms_per_step': round(r['ms_per_step'], 3), 'higher_is_better': True,
     'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-    'config': {'workload': f'{wl} shape, task t={args.task}: C={C}, D={D}, M={cfg["M"]}/task, '
-                           f'P={(args.task + 1) * cfg["M"]}, B={B}, H={H}, F={F}, beta={cfg["beta"]}, Yogi'},
-    'cpu_baseline': {'value': round(r['value'], 4), 'unit': 'steps/s', 'cores': r['cores'], 'kind': 'port',
-                     'sample': f'{r["steps"]} full ELBO steps (fwd+bwd+Yogi) on the oracle port of the reference '
-                               f'algorithm (reference op order), fp32, {r["cores"]} host threads, rank 0 only'},
+    'config': bench_config(wl, args.task, world, None, args.no_shard_factor),
+    'cpu_baseline': {'value': round(r['value'], 4), 'unit': 'steps/s', 'cores': r['cores'], 'kind': r['kind'],
+                     'sample': r['sample'] + ', rank 0 only'},
     'e2e': {'value': round(r['value'], 4), 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     'gpu_launches': 0,
   }
@@ -429,6 +565,7 @@ def main():
   ap.add_argument('--task', type=int, default=None)
   ap.add_argument('--batch', type=int, default=None, help='override the (global) minibatch size of the workload')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-scaled', action='store_true', help='skip the scaled-synthetic sub-record of the default line')
   ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
   ap.add_argument('--no-shard-factor', action='store_true', help='N > 1: keep the O(P^3) factor stage replicated on every rank')
   ap.add_argument('--verbose', action='store_true', help='progress lines on stderr')

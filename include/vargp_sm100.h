@@ -62,6 +62,10 @@ typedef struct {
 int vargp_init(int device);
 const char* vargp_version(void);
 const char* vargp_strerror(int code);
+/* programmatic dependent launch between the library's kernels (on by default; VARGP_PDL=0 in the environment of
+ * vargp_init also disables it).  bench.py switches it off for its serialised per-kernel timing pass.  Returns the
+ * previous setting. */
+int vargp_set_pdl(int on);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t vargp_launch_count(void);
 

@@ -76,20 +76,3 @@ def test_model_parity_on_tcs_and_optional_schedules(name, tcs_ops, monkeypatch):
     assert util.relerr(terms[k], r64[k]) < tol, k
   for k in util.GRAD_KEYS:
     assert util.relerr(grads[k], r64['grads'][k]) < 10 * tol, k
-
-
-@pytest.mark.parametrize('name', ['dkl_t0', 'dkl_t1'])
-def test_dkl_gpu_matches_reference_fixture(name, cuda_ops):
-  """fp32 on the B200 kernels vs the live reference's fp64 numbers (first run pending: the tolerances follow the
-  reference's own fp32-vs-fp64 error of these ill-scaled random-MLP cases)."""
-  from tests.test_dkl_golden import _run
-  rec, terms, grads, probs = _run(name, 'cuda', torch.float32)
-  r32, r64 = rec['f32'], rec['f64']
-  for k, v in terms.items():
-    assert util.relerr(v, r64[k]) < max(1e-4, 10 * util.relerr(r32[k], r64[k])), k
-  scale = max(v.norm().item() for v in r64['grads'].values())
-  for k, v in r64['grads'].items():
-    own = ((r32['grads'][k].double() - v).norm() / max(v.norm().item(), 1e-4 * scale)).item()
-    err = ((grads[k].double().cpu() - v).norm() / max(v.norm().item(), 1e-4 * scale)).item()
-    assert err < max(1e-3, 10 * own), (k, err, own)
-  assert (probs.double().cpu() - r64['probs']).abs().max().item() < max(1e-5, 3 * (r32['probs'].double() - r64['probs']).abs().max().item())

@@ -139,3 +139,17 @@ def test_optional_schedules_are_the_same_function(name, flag, emu_ops, monkeypat
     assert util.relerr(terms[k], ref[k]) < 1e-8, k
   for k in util.GRAD_KEYS:
     assert util.relerr(grads[k], ref['grads'][k]) < 1e-7, k
+
+
+def test_fused_schedule_at_the_benched_size_fp64(emu_ops):
+  """The benched Split-MNIST t=4 step at FULL size (P=300, B=512) through the host schedule in fp64 vs the live
+  reference's stored fp64 outputs (tests/golden/make_large.py; big gradients compared through subsample + projections)."""
+  rec = util.load_golden('large_split_t4')
+  params, prev, x, y, noise, n_v, F, flags = util.case_tensors(rec['case'], torch.float64)
+  ref = rec['f64']
+  gp = util.build_model(params, prev, n_v, F, flags, 'cpu', torch.float64)
+  terms, grads = util.run_model(gp, x, y, noise, rec['beta'], rec['Ntot'])
+  for k in ('kl_hypers', 'kl_u', 'nll', 'total'):
+    assert util.relerr(terms[k], ref[k]) < 1e-8, k
+  for k in util.GRAD_KEYS:
+    assert util.compressed_err(grads[k], ref['grads'][k]) < 1e-7, k

@@ -124,3 +124,38 @@ def test_predict_at_notebook_sizes(cuda_ops):
   assert tuple(probs.shape) == (96, 10)
   assert (probs.double().cpu() - ref).abs().max().item() < 1e-5
   assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+
+
+def test_first_graphed_step_is_exactly_one_update(cuda_ops):
+  """The warm-up steps behind the graph capture must leave no trace: after exactly one `step()` from the
+  same seed the graphed and the eager stepper hold the same parameters, Yogi moments and bias-correction powers."""
+  from vargp_b200.train import ElboStepper
+  out = {}
+  for mode in (False, True):
+    gp, x, y = _model()
+    st = ElboStepper(gp, n_data=2560, batch_size=256, beta=1.0, lr=1e-2, use_graph=mode)
+    torch.manual_seed(7)
+    st.step(x, y)
+    torch.cuda.synchronize()
+    out[mode] = (st.opt.flat_p.clone(), st.opt.m.clone(), st.opt.v.clone(), st.opt.pows.clone(), st.terms_vec.clone())
+  for a, b in zip(out[True], out[False]):
+    assert util.relerr(a, b) < 1e-5
+  assert torch.equal(out[True][3], out[False][3])                 # b1^1, b2^1: exactly one Yogi step
+
+
+def test_stepper_reports_non_pd_after_the_step(cuda_ops):
+  """A non-PD Gram does not raise inside the graph-replayed step, but `stepper.check_errors()` (called by train() once
+  per epoch) does; loss()/predict() outside the stepper keep raising immediately (var_gp/gp_utils.py:10)."""
+  from vargp_b200.train import ElboStepper
+  gp, x, y = _model()
+  st = ElboStepper(gp, n_data=2560, batch_size=256, use_graph=True)
+  st.step(x, y)
+  st.check_errors()
+  assert gp.sync_errors
+  with torch.no_grad():
+    gp.z[0, 0].fill_(float('nan'))
+  st.step(x, y)
+  with pytest.raises(torch.linalg.LinAlgError):
+    st.check_errors()
+  with pytest.raises(torch.linalg.LinAlgError):
+    gp.predict(x)

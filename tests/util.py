@@ -12,7 +12,7 @@ GRAD_KEYS = ('z', 'u_mean', 'u_tril_vec', 'log_mean', 'log_logvar')
 
 def golden_names():
   """VARGP fixtures (make_golden.CASES)."""
-  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith(('retrain_', 'dkl_', 'data_')))
+  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith(('retrain_', 'dkl_', 'data_', 'large_')))
 
 
 def retrain_names():
@@ -113,3 +113,28 @@ def run_retrain_model(gp, x, y, noise, beta, Ntot):
     for k in ('z', 'u_mean', 'u_tril_vec'):
       grads[f'retrain.{s}.{k}'] = gp.retrain_params[s][k].grad
   return dict(kl_hypers=kl_h, kl_u=kl_u, nll=nll, total=total), grads
+
+
+# ------------------------------------------------------------------------------------------------------
+# full-size fixtures (tests/golden/make_large.py): big tensors are stored as norm + strided subsample + projections
+# ------------------------------------------------------------------------------------------------------
+def large_names():
+  return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and f.startswith('large_'))
+
+
+def compressed_err(actual, ref):
+  """Error of `actual` against a reference stored by make_large.compress: the norm-relative error for a plain
+  tensor; for a compressed one the max of (a) the norm-relative error over the stored strided subsample, (b) the
+  relative difference of the norms and (c) the projection residuals |s.(a - b)| / (3 |b|) over the stored random-sign
+  vectors s (for an error vector e, s.e ~ N(0, |e|^2): an error of norm tol*|b| ANYWHERE in the tensor shows up as
+  residuals of that size; the factor 3 keeps a correct tensor from failing on the tail of that distribution)."""
+  if not isinstance(ref, dict):
+    return relerr(actual, ref)
+  from tests.golden.make_large import project
+  flat = actual.detach().double().cpu().reshape(-1)
+  assert tuple(actual.shape) == tuple(ref['shape']), (tuple(actual.shape), ref['shape'])
+  sub = flat[::ref['stride']]
+  e_sub = ((sub - ref['sub']).norm() / ref['sub'].norm().clamp_min(1e-300)).item()
+  e_norm = abs(flat.norm().item() - ref['norm']) / max(ref['norm'], 1e-300)
+  e_proj = ((project(flat, ref['seed']) - ref['proj']).abs().max() / (3.0 * max(ref['norm'], 1e-300))).item()
+  return max(e_sub, e_norm, e_proj)

@@ -26,6 +26,12 @@ extern "C" const char* vargp_strerror(int code) {
 
 extern "C" int64_t vargp_launch_count(void) { return g_launches; }
 
+extern "C" int vargp_set_pdl(int on) {
+  const int old = g_pdl ? 1 : 0;
+  g_pdl = on != 0;
+  return old;
+}
+
 int vargp_tc_init();   // gemm_tc.cu
 
 extern "C" int vargp_init(int device) {

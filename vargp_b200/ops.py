@@ -55,6 +55,7 @@ def _load():
   lib.vargp_strerror.argtypes = [ctypes.c_int]
   lib.vargp_launch_count.restype = i64
   lib.vargp_init.argtypes = [ctypes.c_int]
+  lib.vargp_set_pdl.argtypes = [ctypes.c_int]
   lib.vargp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
   lib.vargp_graph_instantiate.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
   lib.vargp_graph_launch.argtypes = [vp, vp]
@@ -194,6 +195,10 @@ class CudaOps:
   def launch_count(self):
     return int(self.lib.vargp_launch_count())
 
+  def set_pdl(self, on):
+    """Programmatic dependent launch between the library's kernels on / off; returns the previous setting."""
+    return bool(self.lib.vargp_set_pdl(int(bool(on))))
+
   # -- step graph with per-node priorities ------------------------------------------------------
   def graph_instantiate(self, raw_graph, use_node_priority=True):
     """cudaGraph_t (int, e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()) -> cudaGraphExec_t handle."""
@@ -261,9 +266,15 @@ class CudaOps:
     else:
       flops = nbytes = 0.0
     if self.use_tc and (zeroed or not (d.tri_a or d.tri_b)):
+      if self.prof is not None:
+        c2, cs = self.lib.vargp_tc2_launch_count(), self.lib.vargp_tcs_launch_count()
       rc = self._timed(tag, 'gemm_tc', flops, nbytes, lambda: self.lib.vargp_gemm_tc(ctypes.byref(d), s))
       if rc == 0:
         self.tc_calls += 1
+        if self.prof is not None:          # name the kernel that actually ran (1-CTA, 2-CTA persistent, small-shape)
+          kern = ('gemm_tc2' if self.lib.vargp_tc2_launch_count() != c2 else
+                  'gemm_tcs' if self.lib.vargp_tcs_launch_count() != cs else 'gemm_tc')
+          self.prof[-1] = (self.prof[-1][0], kern) + self.prof[-1][2:]
         return
       if self.prof is not None:
         self.prof.pop()

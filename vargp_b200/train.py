@@ -23,6 +23,7 @@ USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
 # per-node priorities away.  Opt-in: measured on B200 at the Split-MNIST shape it changes nothing (731 vs 734 steps/s;
 # profiles/r1d_timeline_node_prio.txt: the critical chain still queues behind the resident CTAs of the side GEMMs).
 USE_NODE_PRIORITY = os.environ.get('VARGP_NODE_PRIO', '0') != '0'
+GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'
 
 
 class ElboStepper:
@@ -41,6 +42,12 @@ class ElboStepper:
     if shard_factor and world_size > 1 and gp.var_mean_mask == 1.0:
       from .elbo import FactorShard
       self.shard = FactorShard()
+    # N > 1: the gradient all-reduce, the factor-shard collectives and the Yogi step are captured into the step graph
+    # too (NCCL kernels are capturable), so a data-parallel step is ONE graph launch like the single-GPU step.
+    # VARGP_GRAPH_NCCL=0 restores the round-1 split (graph up to the backward pass, eager all-reduce + Yogi; no graph
+    # at all with the factor stage sharded).
+    self.graph_nccl = GRAPH_NCCL and world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl'
+    if self.shard is not None and not self.graph_nccl:
       use_graph = False                    # collectives inside forward / backward: launch eagerly
     self.use_graph = use_graph
     self.graph = None
@@ -56,7 +63,10 @@ class ElboStepper:
     self._copy_stream = None
     self.exec = None             # cudaGraphExec_t with per-node priorities (single-GPU graph mode)
     self.noise = None            # static noise buffers, refilled eagerly before every launch of `exec`
-    gp.sync_errors = False
+    self.info = None             # Cholesky status words of the last step (the graph's static buffer in graph mode)
+    self._host_terms = None      # pinned (2, 3) ring of the loss terms fetched by `fetch_terms_async`
+    self._host_ev = [None, None]
+    self._host_n = 0
 
   def _make_noise(self):
     """Static buffers for the step's three draws (same shapes, dtype and order as the draws VARGP.loss issues itself:
@@ -83,11 +93,13 @@ class ElboStepper:
 
   def _grad_body(self):
     self.opt.zero_grad()
-    self.gp.factor_shard = self.shard
+    gp = self.gp
+    sync, gp.sync_errors, gp.factor_shard = gp.sync_errors, False, self.shard   # no host sync inside the step ...
     try:
-      kl_h, kl_u, nll = self.gp.loss(self.x, self.y, noise=self.noise)
+      kl_h, kl_u, nll = gp.loss(self.x, self.y, noise=self.noise)
     finally:
-      self.gp.factor_shard = None
+      gp.sync_errors, gp.factor_shard = sync, None       # ... but predict() / loss() outside it raise as before
+    self.info = gp._last_info
     loss = shard_loss(kl_h, kl_u, nll, self.beta, self.n_data, self.global_batch, self.world, coef=self.coef)
     loss.backward()
     terms = (kl_h.detach(), kl_u.detach(), nll.detach())
@@ -104,13 +116,39 @@ class ElboStepper:
     self._finish()
     return terms
 
+  def _snapshot(self):
+    """Everything a warm-up step mutates: parameters, optimizer state, the device RNG stream."""
+    opt = self.opt
+    if hasattr(opt, 'flat_p'):
+      st = [t.clone() for t in (opt.flat_p, opt.flat_g, opt.m, opt.v, opt.pows)]
+    else:
+      import copy
+      st = ([p.detach().clone() for p in self.gp.parameters()], copy.deepcopy(opt.state_dict()), getattr(opt, '_t', None))
+    return st, torch.cuda.get_rng_state(self.x.device)
+
+  def _restore(self, snap):
+    st, rng = snap
+    opt = self.opt
+    with torch.no_grad():
+      if hasattr(opt, 'flat_p'):
+        for dst, src in zip((opt.flat_p, opt.flat_g, opt.m, opt.v, opt.pows), st):
+          dst.copy_(src)
+      else:
+        for p, q in zip(self.gp.parameters(), st[0]):
+          p.copy_(q)
+        opt.load_state_dict(st[1])
+        if st[2] is not None:
+          opt._t = st[2]
+    torch.cuda.set_rng_state(rng, self.x.device)
+
   def _capture(self):
-    """Single GPU: the whole step is one graph.  Data parallel: the graph ends with the backward pass; the
-    all-reduce of the flat gradient buffer and the (two-launch) Yogi step follow it eagerly, which keeps NCCL out
-    of the capture at the price of three host calls per step instead of one."""
+    """The whole step -- zero_grad, loss, backward, (N > 1: the NCCL gradient all-reduce and the factor-shard
+    collectives,) Yogi -- becomes ONE CUDA graph.  The three warm-up steps that prime the allocator pools, the lazy
+    inits and the NCCL communicator run on real data, so everything they mutate (parameters, Yogi moments and
+    bias-correction powers, the RNG stream) is snapshotted before and restored after: the first `step()` applies
+    exactly one update, like the eager loop of experiments/vargp.py:30-37."""
     from . import ops as _ops_mod
     ops = self._ops = _ops_mod.get_ops()
-    # warm up on a side stream (allocator pools, lazy inits, cuBLAS-free so nothing else to prime)
     # The capture stream has HIGH priority: its kernel nodes inherit it, the nodes of the side branches
     # (elbo._Fork: the minibatch-sized Kzx / Gz1 GEMMs, a few hundred CTAs each) keep the default, lowest one.  The
     # block scheduler then hands SMs to the critical chain (Kzz -> Cholesky -> whitening ...: many short kernels of
@@ -119,6 +157,7 @@ class ElboStepper:
     if node_prio:
       self.noise = self._make_noise()
       self._draw_noise()
+    snap = self._snapshot()
     s = torch.cuda.Stream(priority=-1 if USE_PRIORITY else 0)
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -126,14 +165,18 @@ class ElboStepper:
         self._body()
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
+    self._restore(snap)
+    torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph(keep_graph=True) if node_prio else torch.cuda.CUDAGraph()
+    self._tail_in_graph = self.world == 1 or self.graph_nccl
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
-      self.terms = self._grad_body() if self.world > 1 else self._body()
-    self._graph_terms_vec = self.terms_vec      # static output of the graph
+      self.terms = self._body() if self._tail_in_graph else self._grad_body()
+    self._graph_terms_vec = self.terms_vec      # static outputs of the graph
+    self._graph_info = self.info
     if node_prio:
       self.exec = ops.graph_instantiate(self.graph.raw_cuda_graph(), use_node_priority=True)
-    self.launches_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
+    self.launches_per_step = ops.launch_count() - n0 + (0 if self._tail_in_graph else 2)
 
   def _load_inputs(self, x, y):
     """Inputs of this step into the static buffers: from the staging buffers if (x, y) are the tensors announced
@@ -179,18 +222,51 @@ class ElboStepper:
       out = self._body()
     else:
       if self.graph is None:
-        self._capture()      # note: the capture itself does not advance the parameters
+        self._capture()      # neither the warm-up steps nor the capture advance parameters / optimizer / RNG
       if self.exec is not None:
         self._draw_noise()
         self._ops.graph_launch(self.exec)
       else:
         self.graph.replay()
-      if self.world > 1:
+      if not self._tail_in_graph:
         self._finish()
-      out, self.terms_vec = self.terms, self._graph_terms_vec
+      out, self.terms_vec, self.info = self.terms, self._graph_terms_vec, self._graph_info
     if prefetch is not None:
       self._prefetch(*prefetch)
     return out
+
+  def check_errors(self):
+    """Raise torch.linalg.LinAlgError if the Cholesky of the LAST training step hit a non-positive pivot (one device
+    sync).  The reference raises inside the step (var_gp/gp_utils.py:10); the graph-replayed step cannot, so
+    `train()` calls this once per epoch."""
+    if self.info is not None:
+      bad = int(self.info.max().item())
+      if bad:
+        from .vargp import CholeskyError
+        raise CholeskyError(f'linalg.cholesky: the input is not positive-definite '
+                            f'(leading minor of order {bad} is not positive-definite)')
+
+  def fetch_terms_async(self):
+    """Queue the device-to-host copy of this step's (kl_hypers, kl_u, nll) into a pinned two-slot ring without
+    waiting for it; `host_terms(lag)` hands out a completed slot.  Loggers that read the terms one step late never
+    stall the launch of the next step (the synchronous read costs ~4 % of a Split-MNIST-shape step)."""
+    if self._host_terms is None:
+      self._host_terms = torch.empty(2, 3, dtype=self.terms_vec.dtype).pin_memory()
+    k = self._host_n & 1
+    self._host_terms[k].copy_(self.terms_vec, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    self._host_ev[k] = ev
+    self._host_n += 1
+
+  def host_terms(self, lag=1):
+    """(3,) pinned host tensor with the loss terms of the step `lag` fetches ago (0 = the last one: waits for it);
+    None while fewer steps have been fetched."""
+    if lag not in (0, 1) or self._host_n <= lag:
+      return None
+    k = (self._host_n - 1 - lag) & 1
+    self._host_ev[k].synchronize()
+    return self._host_terms[k]
 
   def __del__(self):
     if getattr(self, 'exec', None) is not None:
@@ -239,17 +315,44 @@ class TensorTask:
     return self.data[idx], self.targets[idx]
 
 
+def set_seeds(seed=None):
+  """var_gp/train_utils.py:13-18."""
+  if seed:
+    import random
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+def _batches(dataset, batch_size, device):
+  """(x, y) minibatches on `device`, in order: slices of the device tensors of a TensorTask, or -- for any other
+  map-style dataset, as the reference's callers pass (var_gp/datasets.py) -- a DataLoader like train_utils.py:22."""
+  if hasattr(dataset, 'x') and hasattr(dataset, 'y'):
+    xs, ys = dataset.x, dataset.y
+    for lo in range(0, len(dataset), batch_size):
+      yield xs[lo:lo + batch_size].to(device), ys[lo:lo + batch_size].to(device)
+  else:
+    from torch.utils.data import DataLoader
+    for x, y in DataLoader(dataset, batch_size=batch_size):
+      yield x.to(device), y.to(device)
+
+
 @torch.no_grad()
 def compute_accuracy(dataset, gp, batch_size=512, device=None, noise_fn=None):
-  """var_gp/train_utils.py:21-35.  `noise_fn(i, B)` may pin the predictive noise of batch i."""
+  """var_gp/train_utils.py:21-35.  `noise_fn(i, B)` may pin the predictive noise of batch i.  Counts stay on the
+  device (one host sync per evaluation instead of one per batch); the reference's NaN assertion is kept."""
   device = device or gp.z.device
   correct = torch.zeros((), dtype=torch.int64, device=device)
-  n, xs, ys = len(dataset), dataset.x, dataset.y
-  for i, lo in enumerate(range(0, n, batch_size)):
-    x, y = xs[lo:lo + batch_size].to(device), ys[lo:lo + batch_size].to(device)
+  nans = torch.zeros((), dtype=torch.bool, device=device)
+  for i, (x, y) in enumerate(_batches(dataset, batch_size, device)):
     preds = gp.predict(x, noise=None if noise_fn is None else noise_fn(i, x.size(0)))
+    nans |= torch.isnan(preds).any()
     correct += (preds.argmax(dim=-1) == y).sum()
-  return correct.item() / n
+  if bool(nans.item()):
+    raise AssertionError('Found NaNs')
+  return correct.item() / len(dataset)
 
 
 @torch.no_grad()
@@ -258,14 +361,15 @@ def compute_acc_ent(dataset, gp, batch_size=512, device=None):
   device = device or gp.z.device
   correct = torch.zeros((), dtype=torch.int64, device=device)
   ent = torch.zeros((), device=device)
-  n, xs, ys = len(dataset), dataset.x, dataset.y
-  for lo in range(0, n, batch_size):
-    x, y = xs[lo:lo + batch_size].to(device), ys[lo:lo + batch_size].to(device)
+  nans = torch.zeros((), dtype=torch.bool, device=device)
+  for x, y in _batches(dataset, batch_size, device):
     preds = gp.predict(x)
-    if torch.isnan(preds).any():
-      raise AssertionError('Found NaNs')
+    nans |= torch.isnan(preds).any()
     correct += (preds.argmax(dim=-1) == y).sum()
     ent += -(preds * preds.clamp_min(1e-38).log()).sum()
+  if bool(nans.item()):
+    raise AssertionError('Found NaNs')
+  n = len(dataset)
   return correct.item() / n, ent.item() / n
 
 
@@ -335,8 +439,9 @@ def train(task_id, train_set, val_set, test_set, ep_var_mean=True, map_est_hyper
     for lo in range(0, N, batch_size):
       idx = perm[lo:lo + batch_size]
       terms = stepper_for(idx.numel()).step(xs[idx], ys[idx])
+    for st in steppers.values():                            # a non-PD Gram surfaces within the epoch (the reference
+      st.check_errors()                                     # raises inside the step, gp_utils.py:10): one sync per epoch
     if (e + 1) % eval_interval == 0:
-      gp.check_errors()
       acc = {k: compute_accuracy(d, gp, device=device) for k, d in (('train', train_set), ('val', val_set),
                                                                     ('test', test_set))}
       summary = {f'task{task_id}/{k}/acc': v for k, v in acc.items()}
@@ -347,6 +452,7 @@ def train(task_id, train_set, val_set, test_set, ep_var_mean=True, map_est_hyper
       stopper(acc['val'], dict(state_dict=snapshot_state(gp), acc_summary=summary, step=e + 1))
       if stopper.is_done():
         break
-  gp.check_errors()
+  for st in steppers.values():
+    st.check_errors()
   info = stopper.info()
   return info['state_dict'] if info is not None else snapshot_state(gp)
