@@ -69,14 +69,6 @@ int vargp_set_pdl(int on);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t vargp_launch_count(void);
 
-/* Step graph with per-node priorities: instantiate a captured cudaGraph_t (`graph`) with
- * cudaGraphInstantiateFlagUseNodePriority (use_node_priority != 0) so that kernel nodes captured from a
- * high-priority stream -- the critical chain of the ELBO step -- are scheduled before the default-priority side
- * branches; launch / destroy the resulting cudaGraphExec_t.  The caller keeps `graph` and its memory pool alive. */
-int vargp_graph_instantiate(void* graph, int use_node_priority, void** exec_out);
-int vargp_graph_launch(void* exec, void* stream);
-int vargp_graph_exec_destroy(void* exec);
-
 int vargp_gemm(const vargp_gemm_t* g, void* stream);
 
 /* tcgen05 / TMA path (3xTF32): same contract as vargp_gemm restricted to K-contiguous operands
@@ -87,12 +79,6 @@ int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
  * vargp_tc2_launch_count: launches of that kernel since load. */
 int64_t vargp_tc2_config(int64_t min_tiles);
 int64_t vargp_tc2_launch_count(void);
-/* Small-shape variant of the 1-CTA kernel (128 x 64 tiles, 2 stages, 256 TMEM columns, two CTAs resident per SM):
- * problems whose 128 x 128 grid would have at most `max_ctas` CTAs take it; < 0 disables it (the default -- the
- * variant is opt-in until measured), INT64_MIN only queries.  Returns the previous setting.  Also settable through
- * the environment (VARGP_TCS_MAX_CTAS) before vargp_init.  vargp_tcs_launch_count: its launches since load. */
-int64_t vargp_tcs_config(int64_t max_ctas);
-int64_t vargp_tcs_launch_count(void);
 /* profiling aid: CTA (0,0,0) of every following 1-CTA vargp_gemm_tc launch writes 8 clock64() stamps of its pipeline
  * (entry, setup, first slab landed, first slab issued, first partial sum, MMAs retired, stored, exit) to `buf`
  * (device memory, >= 8 int64); NULL switches it off. */

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Worker of tests/test_dist_gpu.py -- launched with torchrun, one rank per GPU, NCCL:
+
+  1. the data-parallel gradient (minibatch slices, flat-bucket all-reduce; Kzz/Cholesky/KL replicated, then with the
+     factor stage sharded over (h, c) pairs) equals the single-GPU full-batch gradient and loss terms;
+  2. the step graph that contains the NCCL all-reduce and the Yogi step (and, with the factor stage sharded, the
+     all-gathers / reduce-scatters) follows the same trajectory as the eager data-parallel step.
+Prints one JSON line on rank 0; exits non-zero on any mismatch."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import util                                      # noqa: E402
+from vargp_b200.synthetic import make_case                  # noqa: E402
+from vargp_b200.dist import shard_coef                      # noqa: E402
+from vargp_b200.elbo import FactorShard                     # noqa: E402
+from vargp_b200.train import ElboStepper                    # noqa: E402
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+dist.init_process_group('nccl', device_id=dev)
+out = {}
+
+
+def relerr(a, b):
+  return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+# ---- 1. gradients: N ranks vs one rank on the full batch ----
+for name, kw in (('replicated', dict(C=10, D=784, M=60, t=2, B=128 * world, sigma=10., seed=5)),
+                 ('sharded', dict(C=10, D=784, M=640, t=0, B=256 * world, sigma=10., seed=6))):
+  params, prev, x, y, noise = make_case(**kw)
+  B = x.size(0) // world
+  beta, N = 1.7, 10. * x.size(0)
+  gp = util.build_model(params, prev, 3, 10, {}, dev, torch.float32)
+  nz = {k: v.to(dev) for k, v in noise.items()}
+  kl_h, kl_u, nll = gp.loss(x.to(dev), y.to(dev), noise=nz)                      # full batch on this GPU
+  gp.zero_grad()
+  (beta * kl_h + kl_u + (N / x.size(0)) * nll).backward()
+  full = torch.cat([p.grad.reshape(-1) for p in gp.parameters()]).clone()
+  full_terms = torch.stack([kl_h.detach(), kl_u.detach(), nll.detach()])
+  sl = slice(rank * B, (rank + 1) * B)
+  nzr = dict(nz, eps_f=nz['eps_f'][..., sl].contiguous())
+  sharded = name == 'sharded'
+  gp.factor_shard = FactorShard() if sharded else None
+  a, b, c = shard_coef(beta, N, x.size(0), world, factor_sharded=sharded)
+  kl_h, kl_u, nll = gp.loss(x[sl].to(dev), y[sl].to(dev), noise=nzr)
+  gp.zero_grad()
+  (a * kl_h + b * kl_u + c * nll).backward()
+  gp.factor_shard = None
+  flat = torch.cat([p.grad.reshape(-1) for p in gp.parameters()])
+  dist.all_reduce(flat)
+  terms = torch.stack([kl_h.detach(), kl_u.detach() if sharded else kl_u.detach() / world, nll.detach()])
+  terms[0] /= world
+  dist.all_reduce(terms)
+  out[f'{name}_grad_relerr'] = relerr(flat, full)
+  out[f'{name}_terms_relerr'] = relerr(terms, full_terms)
+
+# ---- 2. NCCL inside the step graph vs the eager data-parallel step ----
+for name, kw in (('graph', dict(C=10, D=784, M=60, t=2, B=128, sigma=10., seed=7)),
+                 ('graph_sharded', dict(C=10, D=784, M=640, t=0, B=256, sigma=10., seed=8))):
+  res = {}
+  for mode in ('eager', 'graph'):
+    params, prev, x, y, _ = make_case(**kw)
+    gp = util.build_model(params, prev, 3, 10, {}, dev, torch.float32)
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = torch.rand(4, kw['B'], 784, generator=g).to(dev)
+    ys = torch.randint(0, 10, (4, kw['B']), generator=g).to(dev)
+    st = ElboStepper(gp, n_data=10 * kw['B'] * world, batch_size=kw['B'], beta=1.7, lr=1e-2, world_size=world,
+                     use_graph=mode == 'graph')
+    torch.manual_seed(11)                       # identical theta draws on every rank
+    for i in range(6):
+      st.step(xs[i % 4], ys[i % 4])
+    st.check_errors()
+    torch.cuda.synchronize()
+    res[mode] = (st.opt.flat_p.clone(), st.terms_vec.clone(), bool(getattr(st, '_tail_in_graph', False)),
+                 st.shard is not None)
+  out[f'{name}_param_relerr'] = relerr(res['graph'][0], res['eager'][0])
+  out[f'{name}_terms_relerr'] = relerr(res['graph'][1], res['eager'][1])
+  out[f'{name}_collectives_in_graph'] = res['graph'][2]
+  out[f'{name}_factor_sharded'] = res['graph'][3]
+  # replicas stay in sync: every rank holds the same parameters after the steps
+  p0 = res['graph'][0].clone()
+  dist.broadcast(p0, 0)
+  out[f'{name}_replica_drift'] = relerr(res['graph'][0], p0)
+
+ok = (out['replicated_grad_relerr'] < 2e-5 and out['sharded_grad_relerr'] < 2e-5 and
+      out['replicated_terms_relerr'] < 1e-5 and out['sharded_terms_relerr'] < 1e-5 and
+      out['graph_param_relerr'] < 1e-5 and out['graph_sharded_param_relerr'] < 1e-5 and
+      out['graph_collectives_in_graph'] and out['graph_sharded_collectives_in_graph'] and
+      out['graph_sharded_factor_sharded'] and not out['graph_factor_sharded'] and
+      out['graph_replica_drift'] == 0.0 and out['graph_sharded_replica_drift'] < 1e-6)
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+if rank == 0:
+  print(json.dumps(dict(world=world, ok=bool(flag.item() == 0), **out)))
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 0 else 1)

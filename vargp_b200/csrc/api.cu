@@ -6,7 +6,6 @@
 namespace vargp {
 int64_t g_launches = 0;
 bool g_pdl = true;
-bool g_prio_attr = false;
 int g_device = -1;
 }  // namespace vargp
 
@@ -46,37 +45,5 @@ extern "C" int vargp_init(int device) {
   g_device = device;
   const char* pdl = getenv("VARGP_PDL");
   if (pdl) g_pdl = atoi(pdl) != 0;
-  const char* pa = getenv("VARGP_PRIO_ATTR");
-  if (pa) g_prio_attr = atoi(pa) != 0;
   return vargp_tc_init();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Step graph with per-node priorities.  A captured step has a critical chain (captured from a high-priority
-// stream) and side branches (default priority); a plain instantiation runs every node at the priority of the
-// LAUNCH stream, cudaGraphInstantiateFlagUseNodePriority keeps the per-node values.  PyTorch's CUDAGraph does not
-// expose that flag, so the host side hands over the captured cudaGraph_t and replays through these three calls.
-// ---------------------------------------------------------------------------------------------
-extern "C" int vargp_graph_instantiate(void* graph, int use_node_priority, void** exec_out) {
-  if (!graph || !exec_out) return VARGP_ERR_ARG;
-  cudaGraphExec_t exec = nullptr;
-  cudaError_t e = cudaGraphInstantiateWithFlags(&exec, (cudaGraph_t)graph,
-                                                use_node_priority ? cudaGraphInstantiateFlagUseNodePriority : 0);
-  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-  *exec_out = exec;
-  return 0;
-}
-
-extern "C" int vargp_graph_launch(void* exec, void* stream) {
-  if (!exec) return VARGP_ERR_ARG;
-  cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)exec, (cudaStream_t)stream);
-  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-  return 0;
-}
-
-extern "C" int vargp_graph_exec_destroy(void* exec) {
-  if (!exec) return 0;
-  cudaError_t e = cudaGraphExecDestroy((cudaGraphExec_t)exec);
-  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-  return 0;
 }

@@ -14,7 +14,6 @@ extern int64_t g_launches;   // counted on the host at every kernel launch (benc
 #define VARGP_ERR_NOT_INIT (-3)
 
 extern bool g_pdl;            // programmatic dependent launch between the library's kernels (VARGP_PDL=0 disables)
-extern bool g_prio_attr;      // VARGP_PRIO_ATTR=1: stamp every launch with its stream's priority explicitly (graph nodes)
 
 // Every kernel of the library starts with pdl_enter(): `launch_dependents` lets the NEXT kernel of the stream (or
 // graph) be scheduled onto SMs as they drain instead of after this grid has fully retired, `wait` blocks until
@@ -35,20 +34,12 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   unsigned n = 0;
   if (g_pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
-  }
-  if (g_prio_attr) {
-    int prio = 0;
-    if (cudaStreamGetPriority(stream, &prio) == cudaSuccess && prio != 0) {
-      attr[n].id = cudaLaunchAttributePriority;
-      attr[n].val.priority = prio;
-      ++n;
-    }
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;

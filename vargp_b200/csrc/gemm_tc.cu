@@ -23,13 +23,9 @@
 // Roofline: tensor pipe (3 TF32 MMAs per product); the split doubles the smem footprint of a slab instead of
 // the HBM/L2 traffic.  Algorithmic flops per launch: 2*M*N*K*batch (x 1/2 per triangular flag).
 //
-// Two instantiations of the same kernel:
-//   <128, 3, 1>  128 x 128 tiles, 3 stages, 192 KiB of shared memory, one CTA per SM                (the default)
-//   < 64, 2, 2>  128 x  64 tiles, 2 stages,  96 KiB, 256 TMEM columns, <= 72 registers: TWO CTAs per SM, so that the
-//                ramp / store phases of one overlap the MMA phase of the other and grids of 150..300 tiles fit one
-//                wave (the P x P products of the Split-MNIST-shaped step are 180..270 tiles of 128 x 128: two waves
-//                for 1.2..1.8 waves of work).  OPT-IN (vargp_tcs_config / VARGP_TCS_MAX_CTAS): written at the end of
-//                round 1 without GPU time left; not yet run on hardware.
+// A 128 x 64-tile, two-CTAs-per-SM instantiation (<64, 2, 2>: 96 KiB of shared memory, 256 TMEM columns) was measured in
+// round 2 at the Split-MNIST shape and LOST (744 vs 755 steps/s: halving the tile doubles the shared-memory reads of
+// the A operand per flop, and the kernel is bound by the 128 B/clk shared-memory port); it was removed.
 #include "tc_common.cuh"
 
 namespace vargp {
@@ -399,11 +395,6 @@ bool tc2_wants(const vargp_gemm_t* g);
 
 using namespace vargp;
 
-// small-shape variant (128 x 64 tiles, two CTAs per SM): used when the 128 x 128 grid would have at most this many CTAs
-static int64_t g_tcs_max_ctas = -1;            // < 0: off (default)
-static int64_t g_tcs_launches = 0;
-static bool g_tcs_ok = false;
-
 int vargp_tc_init() {
   if (g_tc_ready) return 0;
   void* fn = nullptr;
@@ -413,26 +404,10 @@ int vargp_tc_init() {
   g_encode = (EncodeTiledFn)fn;
   e = cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  // the opt-in small-shape variant must never take the default path down: if its attributes cannot be set it stays off
-  g_tcs_ok = cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<64, 2>::SMEM_BYTES) == cudaSuccess &&
-             cudaFuncSetAttribute(gemm_tc_kernel<64, 2, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-  if (!g_tcs_ok) cudaGetLastError();
-  const char* env = getenv("VARGP_TCS_MAX_CTAS");
-  if (env) g_tcs_max_ctas = atoll(env);
   int rc = tc2_init();
   if (rc) return rc;
   g_tc_ready = true;
   return 0;
-}
-
-/* 128 x 64-tile, two-CTAs-per-SM variant of the 1-CTA kernel: problems whose 128 x 128 grid has at most `max_ctas` CTAs
- * take it; < 0 disables it (default), INT64_MIN only queries.  Returns the previous setting. */
-extern "C" int64_t vargp_tcs_config(int64_t max_ctas) {
-  const int64_t old = g_tcs_max_ctas;
-  if (max_ctas != INT64_MIN) g_tcs_max_ctas = max_ctas;
-  return old;
 }
 
 extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
@@ -462,32 +437,22 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   p.a_mn = (a_k && !(a_mn && g->K == 1)) ? 0 : 1;
   p.b_mn = (b_k && !(b_mn && g->K == 1)) ? 0 : 1;
 
-  const int64_t ctas128 = ceil_div(g->N, 128) * ceil_div(g->M, TC_BM) * nbatch;
   const bool big = tc2_wants(g);
-  const bool small = !big && g_tcs_ok && g_tcs_max_ctas >= 0 && ctas128 <= g_tcs_max_ctas;
 
   alignas(64) CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->M, g->K, g->a_rs, g->a_cs, g->nb, g->a_bs, p.a_mn, p.a_b);
   if (rc) return rc;
   // B(k, n): "rows" of the operand are n; row stride = b_cs, k stride = b_rs
-  rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b, small ? 64 : TC_ROWS);
+  rc = make_map(&tmB, g->B, g->N, g->K, g->b_cs, g->b_rs, g->nb, g->b_bs, p.b_mn, p.b_b, TC_ROWS);
   if (rc) return rc;
 
   // large problems: persistent 2-CTA kernel with 256 x 256 tiles (gemm_tc2.cu)
   if (big) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
 
-  if (small) {
-    dim3 grid((unsigned)ceil_div(g->N, 64), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
-    launch_k(gemm_tc_kernel<64, 2, 2>, dim3(grid), dim3(TC_THREADS), TcCfg<64, 2>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
-    ++g_tcs_launches;
-    return launch_status();
-  }
   dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
   launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
   return launch_status();
 }
-
-extern "C" int64_t vargp_tcs_launch_count(void) { return g_tcs_launches; }
 
 /* profiling aid: device buffer of >= 8 int64 that CTA (0,0,0) of every following vargp_gemm_tc launch (1-CTA kernel)
  * fills with clock64() stamps: entry, setup done, first slab landed, first slab issued, first partial sum ready,

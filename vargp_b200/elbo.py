@@ -43,14 +43,14 @@ class _Ctx:
 _SIDE = {}
 USE_SIDE_STREAM = os.environ.get('VARGP_STREAMS', '1') != '0'
 KZZ_FIRST = os.environ.get('VARGP_KZZ_FIRST', '1') != '0'
-# Opt-in schedule experiments (semantics covered by the CPU host-schedule tests; not yet measured on a B200):
-#   VARGP_STACK_CLASSES=1  x is shared by all classes, so Kzx and Gz1 = (Kxbar . Kzx) xs are ONE (C P) x B / (C P) x D
+# Schedule knobs, measured on B200 at the Split-MNIST shape in round 2 (profiles/r2a_ab.txt): both on = 786 vs 756 steps/s.
+#   VARGP_STACK_CLASSES    x is shared by all classes, so Kzx and Gz1 = (Kxbar . Kzx) xs are ONE (C P) x B / (C P) x D
 #                          product per hyper sample instead of C products with P rows each: at P = 300 that is 24
 #                          instead of 30 row tiles of 128 (the per-class tiling pads 300 rows to 384).
-#   VARGP_V_SIDE=1         V = W Kzx on the side stream right behind Kzx (waiting for an event recorded after the
+#   VARGP_V_SIDE           V = W Kzx on the side stream right behind Kzx (waiting for an event recorded after the
 #                          factorisation), so that it overlaps the T / nu / KL / N chain instead of following it.
-STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '0') != '0'
-V_SIDE = os.environ.get('VARGP_V_SIDE', '0') != '0'
+STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '1') != '0'
+V_SIDE = os.environ.get('VARGP_V_SIDE', '1') != '0'
 
 
 class _Fork:

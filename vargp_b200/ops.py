@@ -57,16 +57,10 @@ def _load():
   lib.vargp_init.argtypes = [ctypes.c_int]
   lib.vargp_set_pdl.argtypes = [ctypes.c_int]
   lib.vargp_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp]
-  lib.vargp_graph_instantiate.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
-  lib.vargp_graph_launch.argtypes = [vp, vp]
-  lib.vargp_graph_exec_destroy.argtypes = [vp]
   lib.vargp_gemm_tc.argtypes = [ctypes.POINTER(GemmDesc), vp]
   lib.vargp_tc2_config.argtypes = [i64]
   lib.vargp_tc2_config.restype = i64
   lib.vargp_tc2_launch_count.restype = i64
-  lib.vargp_tcs_config.argtypes = [i64]
-  lib.vargp_tcs_config.restype = i64
-  lib.vargp_tcs_launch_count.restype = i64
   lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
@@ -199,35 +193,12 @@ class CudaOps:
     """Programmatic dependent launch between the library's kernels on / off; returns the previous setting."""
     return bool(self.lib.vargp_set_pdl(int(bool(on))))
 
-  # -- step graph with per-node priorities ------------------------------------------------------
-  def graph_instantiate(self, raw_graph, use_node_priority=True):
-    """cudaGraph_t (int, e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()) -> cudaGraphExec_t handle."""
-    out = vp()
-    self._check(self.lib.vargp_graph_instantiate(vp(raw_graph), int(bool(use_node_priority)), ctypes.byref(out)),
-                'vargp_graph_instantiate')
-    return out
-
-  def graph_launch(self, exec_handle, stream=None):
-    st = torch.cuda.current_stream() if stream is None else stream
-    self._check(self.lib.vargp_graph_launch(exec_handle, vp(st.cuda_stream)), 'vargp_graph_launch')
-
-  def graph_exec_destroy(self, exec_handle):
-    self.lib.vargp_graph_exec_destroy(exec_handle)
-
   def tc2_config(self, min_tiles=None):
     """Set (or with None query) the tile-count threshold above which GEMMs take the 2-CTA kernel; < 0 disables."""
     return int(self.lib.vargp_tc2_config(-2 ** 63 if min_tiles is None else int(min_tiles)))
 
   def tc2_launch_count(self):
     return int(self.lib.vargp_tc2_launch_count())
-
-  def tcs_config(self, max_ctas=None):
-    """Set (or with None query) the CTA-count threshold below which GEMMs take the 128 x 64-tile, two-CTAs-per-SM
-    variant of the 1-CTA kernel; < 0 disables it (default)."""
-    return int(self.lib.vargp_tcs_config(-2 ** 63 if max_ctas is None else int(max_ctas)))
-
-  def tcs_launch_count(self):
-    return int(self.lib.vargp_tcs_launch_count())
 
   # -- GEMM -----------------------------------------------------------------------------------
   def _desc(self, A, B, C, alpha, beta, a_tri, b_tri, c_tri):
@@ -267,13 +238,12 @@ class CudaOps:
       flops = nbytes = 0.0
     if self.use_tc and (zeroed or not (d.tri_a or d.tri_b)):
       if self.prof is not None:
-        c2, cs = self.lib.vargp_tc2_launch_count(), self.lib.vargp_tcs_launch_count()
+        c2 = self.lib.vargp_tc2_launch_count()
       rc = self._timed(tag, 'gemm_tc', flops, nbytes, lambda: self.lib.vargp_gemm_tc(ctypes.byref(d), s))
       if rc == 0:
         self.tc_calls += 1
-        if self.prof is not None:          # name the kernel that actually ran (1-CTA, 2-CTA persistent, small-shape)
-          kern = ('gemm_tc2' if self.lib.vargp_tc2_launch_count() != c2 else
-                  'gemm_tcs' if self.lib.vargp_tcs_launch_count() != cs else 'gemm_tc')
+        if self.prof is not None:          # name the kernel that actually ran (1-CTA or persistent 2-CTA)
+          kern = 'gemm_tc2' if self.lib.vargp_tc2_launch_count() != c2 else 'gemm_tc'
           self.prof[-1] = (self.prof[-1][0], kern) + self.prof[-1][2:]
         return
       if self.prof is not None:

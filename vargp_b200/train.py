@@ -18,11 +18,6 @@ from .dist import shard_coef, shard_loss
 from .optim import FlatYogi
 
 USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
-# VARGP_NODE_PRIO=1: replay the step graph through libvargp_sm100.so's cudaGraphInstantiateFlagUseNodePriority exec
-# (single-GPU steps).  PyTorch's own instantiation runs every node at the launch stream's priority, which throws the
-# per-node priorities away.  Opt-in: measured on B200 at the Split-MNIST shape it changes nothing (731 vs 734 steps/s;
-# profiles/r1d_timeline_node_prio.txt: the critical chain still queues behind the resident CTAs of the side GEMMs).
-USE_NODE_PRIORITY = os.environ.get('VARGP_NODE_PRIO', '0') != '0'
 GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'
 
 
@@ -61,42 +56,17 @@ class ElboStepper:
     self.terms_vec = None        # (kl_hypers, kl_u, nll) of the last step as one (3,) device tensor
     self._pf = None              # prefetch state: (x_src, y_src, x_staging, y_staging, ready event)
     self._copy_stream = None
-    self.exec = None             # cudaGraphExec_t with per-node priorities (single-GPU graph mode)
-    self.noise = None            # static noise buffers, refilled eagerly before every launch of `exec`
     self.info = None             # Cholesky status words of the last step (the graph's static buffer in graph mode)
     self._host_terms = None      # pinned (2, 3) ring of the loss terms fetched by `fetch_terms_async`
     self._host_ev = [None, None]
     self._host_n = 0
-
-  def _make_noise(self):
-    """Static buffers for the step's three draws (same shapes, dtype and order as the draws VARGP.loss issues itself:
-    hypers -> u_<t -> likelihood).  A graph launched outside torch.cuda.CUDAGraph.replay() cannot
-    contain torch RNG kernels (replay() is what advances their Philox offsets), so the node-priority exec takes
-    its noise from these buffers and `_draw_noise` refills them on the stream right before each launch."""
-    gp = self.gp
-    dev, dt = self.x.device, gp.z.dtype
-    new = lambda *sh: torch.empty(*sh, device=dev, dtype=dt)
-    C, B = gp.z.size(0), self.x.size(0)
-    H = 1 if gp.kernel.map_est else gp.n_v
-    nz = dict()
-    if not gp.kernel.map_est:
-      nz['eps_theta'] = new(gp.n_v, gp.kernel.log_mean.numel())
-    if gp.n_prev:
-      nz['eps_u'] = new(gp.n_v, H, C, gp.n_prev * gp.M)
-    nz['eps_f'] = new(H, gp.likelihood.n_f, C, B)
-    return nz
-
-  def _draw_noise(self):
-    for k in ('eps_theta', 'eps_u', 'eps_f'):
-      if k in self.noise:
-        self.noise[k].normal_()
 
   def _grad_body(self):
     self.opt.zero_grad()
     gp = self.gp
     sync, gp.sync_errors, gp.factor_shard = gp.sync_errors, False, self.shard   # no host sync inside the step ...
     try:
-      kl_h, kl_u, nll = gp.loss(self.x, self.y, noise=self.noise)
+      kl_h, kl_u, nll = gp.loss(self.x, self.y)
     finally:
       gp.sync_errors, gp.factor_shard = sync, None       # ... but predict() / loss() outside it raise as before
     self.info = gp._last_info
@@ -153,10 +123,6 @@ class ElboStepper:
     # (elbo._Fork: the minibatch-sized Kzx / Gz1 GEMMs, a few hundred CTAs each) keep the default, lowest one.  The
     # block scheduler then hands SMs to the critical chain (Kzz -> Cholesky -> whitening ...: many short kernels of
     # <= 30..270 CTAs) first, and the side GEMMs fill what is left instead of making the chain queue behind them.
-    node_prio = USE_PRIORITY and USE_NODE_PRIORITY and self.world == 1
-    if node_prio:
-      self.noise = self._make_noise()
-      self._draw_noise()
     snap = self._snapshot()
     s = torch.cuda.Stream(priority=-1 if USE_PRIORITY else 0)
     s.wait_stream(torch.cuda.current_stream())
@@ -167,15 +133,13 @@ class ElboStepper:
     torch.cuda.synchronize()
     self._restore(snap)
     torch.cuda.synchronize()
-    self.graph = torch.cuda.CUDAGraph(keep_graph=True) if node_prio else torch.cuda.CUDAGraph()
+    self.graph = torch.cuda.CUDAGraph()
     self._tail_in_graph = self.world == 1 or self.graph_nccl
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._body() if self._tail_in_graph else self._grad_body()
     self._graph_terms_vec = self.terms_vec      # static outputs of the graph
     self._graph_info = self.info
-    if node_prio:
-      self.exec = ops.graph_instantiate(self.graph.raw_cuda_graph(), use_node_priority=True)
     self.launches_per_step = ops.launch_count() - n0 + (0 if self._tail_in_graph else 2)
 
   def _load_inputs(self, x, y):
@@ -217,17 +181,11 @@ class ElboStepper:
     (the caller must leave those host tensors untouched until then, as with any non_blocking copy)."""
     self._load_inputs(x, y)
     if not self.use_graph:
-      if self.noise is not None:
-        self._draw_noise()
       out = self._body()
     else:
       if self.graph is None:
         self._capture()      # neither the warm-up steps nor the capture advance parameters / optimizer / RNG
-      if self.exec is not None:
-        self._draw_noise()
-        self._ops.graph_launch(self.exec)
-      else:
-        self.graph.replay()
+      self.graph.replay()
       if not self._tail_in_graph:
         self._finish()
       out, self.terms_vec, self.info = self.terms, self._graph_terms_vec, self._graph_info
@@ -267,13 +225,6 @@ class ElboStepper:
     k = (self._host_n - 1 - lag) & 1
     self._host_ev[k].synchronize()
     return self._host_terms[k]
-
-  def __del__(self):
-    if getattr(self, 'exec', None) is not None:
-      try:
-        self._ops.graph_exec_destroy(self.exec)
-      except Exception:
-        pass
 
 
 # ------------------------------------------------------------------------------------------------------
