@@ -179,10 +179,12 @@ int vargp_rbf_bwd_xside(const float* xs, const float* csum, const float* Gx,
 
 /* Monte-Carlo softmax likelihood (var_gp/likelihoods.py:13-47), forward and adjoint in one pass:
  * nll += -(1/HF) sum_hfb log softmax_C(f_mean + sqrt(f_var) eps)[y_b];  g_mean, g_var = d nll / d(f_mean, f_var).
- * eps (H,F,C,B); y int64 (B). */
+ * eps (H,F,C,B); y int64 (B).  The sum is deterministic (per-CTA partial sums combined in a fixed order, no float
+ * atomics): `work` holds vargp_softmax_nll_work(H, B) floats; work[0] must be 0 at launch and is 0 again at exit. */
+int64_t vargp_softmax_nll_work(int64_t H, int64_t B);
 int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps, const int64_t* y,
                       int64_t H, int64_t F, int64_t C, int64_t B,
-                      float* nll, float* g_mean, float* g_var, void* stream);
+                      float* nll, float* g_mean, float* g_var, float* work, void* stream);
 /* probs[b][c] = (1/HF) sum_hf softmax_C(f)[c]   (var_gp/likelihoods.py:49-63) */
 int vargp_softmax_predict(const float* f_mean, const float* f_var, const float* eps,
                           int64_t H, int64_t F, int64_t C, int64_t B, float* probs, void* stream);

@@ -231,7 +231,7 @@ def test_tril_unpack(cuda_ops, C, M):
 
 
 @pytest.mark.parametrize('H,C,S,M,B,D', [(3, 10, 3, 20, 200, 784), (2, 3, 1, 7, 33, 37), (1, 4, 2, 9, 21, 16),
-                                         (2, 2, 1, 300, 40, 16)])
+                                         (2, 2, 1, 300, 40, 16), (3, 10, 5, 60, 512, 784), (1, 2, 2, 100, 5000, 16)])
 def test_marginal_kl_kernels(cuda_ops, H, C, S, M, B, D):
   P = S * M
   W = (rnd(H, C, P, P, seed=1, scale=0.1).tril() + torch.eye(P, dtype=torch.float64))
@@ -278,7 +278,8 @@ def test_marginal_kl_kernels(cuda_ops, H, C, S, M, B, D):
   close(Xd, X64, 1e-6, 'sym_mirror')
 
 
-@pytest.mark.parametrize('H,C,P,B,D', [(3, 10, 60, 200, 784), (2, 3, 21, 33, 37), (1, 4, 18, 21, 2)])
+@pytest.mark.parametrize('H,C,P,B,D', [(3, 10, 60, 200, 784), (2, 3, 21, 33, 37), (1, 4, 18, 21, 2), (3, 10, 300, 512, 784),
+                                       (5, 2, 70, 1028, 20), (2, 2, 44, 1100, 8)])
 def test_rbf_adjoint_kernels(cuda_ops, H, C, P, B, D):
   theta = rnd(H, D + 1, seed=1, scale=0.1)
   zs, xs = rnd(H, C, P, D, seed=2), rnd(H, B, D, seed=3)

@@ -128,7 +128,7 @@ def test_rng_draw_order_matches_reference(cuda_ops):
   torch.manual_seed(123)
   b = gp.loss(x.cuda(), y.cuda())
   assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-  assert util.relerr(a[2], b[2]) < 1e-6        # the nll partial sums are combined with float atomics
+  assert torch.equal(a[2], b[2])               # every forward reduction is deterministic (two-stage sums, no float atomics)
 
 
 def test_linearity_and_idempotence_at_scale(cuda_ops):
@@ -141,8 +141,7 @@ def test_linearity_and_idempotence_at_scale(cuda_ops):
   xc, yc = x.cuda(), y.cuda()
   a = gp.loss(xc, yc, noise=nz)
   b = gp.loss(xc, yc, noise=nz)
-  assert util.relerr(a[1], b[1]) < 1e-6                           # kl_u sums with atomics
-  assert abs(float(a[2] - b[2])) <= 1e-6 * abs(float(a[2]))     # nll sums with atomics
+  assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])      # deterministic forward: bit-identical replay
   h = 1024
   n1 = dict(nz, eps_f=nz['eps_f'][..., :h].contiguous())
   n2 = dict(nz, eps_f=nz['eps_f'][..., h:].contiguous())

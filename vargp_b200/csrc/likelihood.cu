@@ -10,9 +10,11 @@ __global__ void __launch_bounds__(128)
 softmax_nll_kernel(const float* __restrict__ f_mean, const float* __restrict__ f_var,
                    const float* __restrict__ eps, const int64_t* __restrict__ y,
                    int64_t H, int64_t F, int64_t C, int64_t B,
-                   float* __restrict__ nll, float* __restrict__ g_mean, float* __restrict__ g_var) {
+                   float* __restrict__ nll, float* __restrict__ g_mean, float* __restrict__ g_var,
+                   float* __restrict__ work) {
   pdl_enter();
   __shared__ float scratch[32];
+  __shared__ bool s_last;
   const int64_t h = blockIdx.y;
   const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
   const bool live = b < B;
@@ -68,9 +70,30 @@ softmax_nll_kernel(const float* __restrict__ f_mean, const float* __restrict__ f
       }
     }
     acc *= scale;
+    if ((unsigned)yb >= (unsigned)C) acc = __int_as_float(0x7fc00000);   // label outside [0, C): F.nll_loss raises; here the loss is NaN
   }
+  // deterministic two-stage sum (no float atomics): every CTA leaves its partial in work[1 + cta]; the CTA that draws
+  // the last ticket adds them up in a fixed order.  work[0] is the ticket counter: zero at launch, zero again at exit.
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(nll, acc);
+  const unsigned nparts = gridDim.x * gridDim.y;
+  unsigned* ticket = reinterpret_cast<unsigned*>(work);
+  float* part = work + 1;
+  if (threadIdx.x == 0) {
+    part[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == nparts - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned i = threadIdx.x; i < nparts; i += 128) t += __ldcg(part + i);
+    t = block_sum(t, scratch);
+    if (threadIdx.x == 0) {
+      nll[0] += t;
+      *ticket = 0u;
+    }
+  }
 }
 
 template <int CMAX>
@@ -125,19 +148,21 @@ softmax_predict_kernel(const float* __restrict__ f_mean, const float* __restrict
 
 using namespace vargp;
 
+extern "C" int64_t vargp_softmax_nll_work(int64_t H, int64_t B) { return 1 + H * ceil_div(B, 128); }
+
 extern "C" int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps, const int64_t* y,
                                  int64_t H, int64_t F, int64_t C, int64_t B, float* nll, float* g_mean,
-                                 float* g_var, void* stream) {
-  if (!f_mean || !f_var || !eps || !y || !nll || !g_mean || !g_var) return VARGP_ERR_ARG;
+                                 float* g_var, float* work, void* stream) {
+  if (!f_mean || !f_var || !eps || !y || !nll || !g_mean || !g_var || !work) return VARGP_ERR_ARG;
   if (H < 1 || F < 1 || C < 1 || B < 0) return VARGP_ERR_ARG;
   if (C > 32 || H > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)H);
   cudaStream_t s = (cudaStream_t)stream;
-  if (C <= 4) launch_k((softmax_nll_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else if (C <= 10) launch_k((softmax_nll_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else if (C <= 16) launch_k((softmax_nll_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
-  else launch_k((softmax_nll_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var);
+  if (C <= 4) launch_k((softmax_nll_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
+  else if (C <= 10) launch_k((softmax_nll_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
+  else if (C <= 16) launch_k((softmax_nll_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
+  else launch_k((softmax_nll_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
   return launch_status();
 }
 

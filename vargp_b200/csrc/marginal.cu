@@ -44,6 +44,52 @@ marginal_reduce_kernel(const float* __restrict__ V, const float* __restrict__ NV
   f_var[g * B + b] = gamma2 + ((q[0] + q[1]) + (q[2] + q[3]));
 }
 
+// Same contract for SMALL problems (Split / Permuted-MNIST shapes: a few MB that sit in L2).  One thread per column
+// walking all P rows is latency-bound there (P / 4 dependent round trips to L2 on 120 CTAs: 37 us at P = 300); here a
+// CTA owns 32 columns and its 8 warps split the rows (P / 32 round trips, 4 x as many CTAs), then reduce through smem.
+__global__ void __launch_bounds__(256)
+marginal_reduce_split_kernel(const float* __restrict__ V, const float* __restrict__ NV, const float* __restrict__ nu,
+                             const float* __restrict__ theta, int64_t theta_rs, int64_t D, int64_t C, int64_t P,
+                             int64_t B, float* __restrict__ f_mean, float* __restrict__ f_var) {
+  pdl_enter();
+  __shared__ float s_m[8][33], s_q[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t g = blockIdx.y;
+  const int64_t b = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = b < B;
+  const float* v = V + g * P * B + b;
+  const float* nv = NV + g * P * B + b;
+  const float* nug = nu + g * P;
+  float m[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t p0 = w; p0 < P; p0 += 32) {
+    float vv[4], nn[4], nn_[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = p0 + 8 * u;
+      const bool ok = live && p < P;
+      vv[u] = ok ? v[p * B] : 0.f;
+      nn[u] = ok ? nv[p * B] : 0.f;
+      nn_[u] = p < P ? __ldg(nug + p) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      m[u] = fmaf(nn_[u], vv[u], m[u]);
+      q[u] = fmaf(vv[u], nn[u] - vv[u], q[u]);
+    }
+  }
+  s_m[w][lane] = (m[0] + m[1]) + (m[2] + m[3]);
+  s_q[w][lane] = (q[0] + q[1]) + (q[2] + q[3]);
+  __syncthreads();
+  if (w == 0 && live) {
+    float ms = 0.f, qs = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ms += s_m[k][lane]; qs += s_q[k][lane]; }
+    const float gamma2 = expf(2.f * theta[(g / C) * theta_rs + D]);
+    f_mean[g * B + b] = ms;
+    f_var[g * B + b] = gamma2 + qs;
+  }
+}
+
 // Vbar = nu gm^T + 2 gv (NV - V)  (Vbar may alias NV);  Vg = gv V;  theta_bar[h][D] += 2 gamma2 sum_{c,b} gv
 // grid (B tiles of 128*VEC, P chunks of kPrepPch rows, G); VEC = 4: float4 along the minibatch axis.
 // Algorithmic bytes 4*(4*G*P*B + 2*G*B).
@@ -200,7 +246,8 @@ kl_fwd_sum_kernel(const float* __restrict__ part, int64_t n, int64_t H, float* _
   if (threadIdx.x == 0) kl[0] += acc / (float)H;
 }
 
-// grid (row chunks, H*C)
+// grid (element chunks of 256 over the M x M block, H*C): one thread per element of T_t (a row loop per CTA was
+// latency-bound: 30 us at M = 60); chunk 0 also handles the O(M) terms
 __global__ void __launch_bounds__(256)
 kl_bwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const float* __restrict__ nu,
               const float* __restrict__ g_kl, int64_t H, int64_t C, int64_t P, int64_t M,
@@ -210,8 +257,10 @@ kl_bwd_kernel(const float* __restrict__ W, const float* __restrict__ T, const fl
   const float s = g_kl[0] / (float)H;
   const float* t = T + (g * S + (S - 1)) * M * M;
   float* tb = Tbar + (g * S + (S - 1)) * M * M;
-  for (int64_t i = blockIdx.x; i < M; i += gridDim.x)
-    for (int64_t j = threadIdx.x; j <= i; j += blockDim.x) tb[i * M + j] = fmaf(s, t[i * M + j], tb[i * M + j]);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * M; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / M, j = e - i * M;
+    if (j <= i) tb[e] = fmaf(s, t[e], tb[e]);
+  }
   if (blockIdx.x == 0) {
     for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
       nubar[g * P + Q + i] = fmaf(s, nu[g * P + Q + i], nubar[g * P + Q + i]);
@@ -275,6 +324,11 @@ extern "C" int vargp_marginal_reduce(const float* V, const float* NV, const floa
   if (!V || !NV || !nu || !theta || !f_mean || !f_var) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
+  if (ceil_div(B, 128) * H * C < 148 * 8) {     // less than one full wave of the streaming kernel: split the rows too
+    dim3 grid((unsigned)ceil_div(B, 32), (unsigned)(H * C));
+    launch_k(marginal_reduce_split_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, V, NV, nu, theta, theta_rs, D, C, P, B, f_mean, f_var);
+    return launch_status();
+  }
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)(H * C));
   launch_k(marginal_reduce_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, V, NV, nu, theta, theta_rs, D, C, P, B, f_mean, f_var);
   return launch_status();
@@ -327,7 +381,8 @@ extern "C" int vargp_kl_bwd(const float* W, const float* T, const float* nu, con
                             int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream) {
   if (!W || !T || !nu || !g_kl || !Wbar || !Tbar || !nubar || M < 1 || P % M) return VARGP_ERR_ARG;
   if (H * C > 65535) return VARGP_ERR_UNSUPPORTED;
-  const unsigned chunks = (unsigned)(M < 64 ? 1 : (M / 32 > 128 ? 128 : M / 32));
+  const int64_t want = ceil_div(M * M, 256);
+  const unsigned chunks = (unsigned)(want > 256 ? 256 : want);
   launch_k(kl_bwd_kernel, dim3(dim3(chunks, (unsigned)(H * C))), dim3(256), 0, (cudaStream_t)stream, W, T, nu, g_kl, H, C, P, M, Wbar,
                                                                                    Tbar, nubar);
   return launch_status();

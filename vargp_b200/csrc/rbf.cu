@@ -144,6 +144,93 @@ rbf_bwd_prep_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64
   }
 }
 
+// Same contract for narrow matrices (Pb <= 32 * VEC * kRowsK columns: the Split / Permuted-MNIST shapes).  The
+// column-per-thread kernel above leaves most lanes idle there (Pb = 300: the second 256-column tile is 83 % empty),
+// needs atomics + a memset for the row sums and walks its rows serially.  Here a WARP owns a row (lanes stride over
+// float4 column groups), row sums are one warp reduction and a plain store (deterministic), and the column sums of the
+// CTA's 32 rows are combined in shared memory before they go out as one atomic per column and CTA.
+// grid (row blocks of 32, G); 8 warps x 4 rows.
+constexpr int kRowsK = 8;            // column groups per lane
+template <int VEC>
+__global__ void __launch_bounds__(256)
+rbf_bwd_prep_rows_kernel(float* __restrict__ Kbar, const float* __restrict__ K, int64_t C, int64_t Pa, int64_t Pb,
+                         float* __restrict__ rsum, float* __restrict__ csum, float* __restrict__ dsum) {
+  pdl_enter();
+  extern __shared__ __align__(16) float s_c[];      // [8][Pb] when csum != nullptr
+  const int64_t g = blockIdx.y;
+  const int64_t h = g / C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float cacc[kRowsK][VEC];
+#pragma unroll
+  for (int k = 0; k < kRowsK; ++k)
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) cacc[k][u] = 0.f;
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = (int64_t)blockIdx.x * 32 + wid * 4 + r;
+    if (i >= Pa) break;                                 // warp-uniform
+    float* kb = Kbar + (g * Pa + i) * Pb;
+    const float* kk = K + (g * Pa + i) * Pb;
+    float w[kRowsK][VEC];
+#pragma unroll
+    for (int k = 0; k < kRowsK; ++k) {
+      const int64_t j0 = ((int64_t)k * 32 + lane) * VEC;
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) w[k][u] = 0.f;
+      if (j0 < Pb) {
+        if (VEC == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(kb + j0);
+          const float4 b = *reinterpret_cast<const float4*>(kk + j0);
+          w[k][0] = a.x * b.x; w[k][1] = a.y * b.y; w[k][2] = a.z * b.z; w[k][3] = a.w * b.w;
+        } else {
+          w[k][0] = kb[j0] * kk[j0];
+        }
+      }
+    }
+    float rpart = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRowsK; ++k) {
+      const int64_t j0 = ((int64_t)k * 32 + lane) * VEC;
+      if (j0 < Pb) {
+        if (dsum) {                 // symmetric Gram: the diagonal only carries the gamma gradient
+#pragma unroll
+          for (int u = 0; u < VEC; ++u)
+            if (j0 + u == i) {
+              dsum[g * Pa + i] = w[k][u];
+              w[k][u] = 0.f;
+            }
+        }
+        if (VEC == 4) *reinterpret_cast<float4*>(kb + j0) = make_float4(w[k][0], w[k][1], w[k][2], w[k][3]);
+        else kb[j0] = w[k][0];
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+          cacc[k][u] += w[k][u];
+          rpart += w[k][u];
+        }
+      }
+    }
+    rpart = warp_sum(rpart);
+    if (lane == 0) rsum[g * Pa + i] = rpart;
+  }
+  if (csum) {
+#pragma unroll
+    for (int k = 0; k < kRowsK; ++k) {
+      const int64_t j0 = ((int64_t)k * 32 + lane) * VEC;
+      if (j0 < Pb) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) s_c[wid * Pb + j0 + u] = cacc[k][u];
+      }
+    }
+    __syncthreads();
+    for (int64_t j = threadIdx.x; j < Pb; j += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) v += s_c[w8 * Pb + j];
+      atomicAdd(csum + h * Pb + j, v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // zs_bar = -(r1 + 2 r2) zs + Gz1 + 2 Gz2 ; Zbar[c][i][d] = sum_h zs_bar exp(-theta[h][d])
 // theta_bar[h][d] += sum_{c,i} (-zs zs_bar - zs Gz1) ; theta_bar[h][D] += 2 sum_{c,i} (r1 + r2)
@@ -215,6 +302,90 @@ rbf_bwd_finish_kernel(const float* __restrict__ zs, const float* __restrict__ Gz
   }
 }
 
+// Same contract, float4 along d, for H <= 4 and D % 4 == 0.  The kernel above issues one atomic per (thread, h) on
+// theta_bar: 375 CTAs hammer the same 3 x 784 addresses at the Split-MNIST shape (50 us for 85 MB that sit in L2).
+// Here a CTA covers 32 rows x 128 d (8 warps x 4 rows, lanes x float4), reduces its theta partial sums over the 8 warps
+// in shared memory and issues one atomic per (h, d) and CTA.
+// grid (D tiles of 128, row blocks of 32).
+constexpr int kFin4Rows = 4;       // rows per warp
+__global__ void __launch_bounds__(256)
+rbf_bwd_finish_v4_kernel(const float* __restrict__ zs, const float* __restrict__ Gz1, const float* __restrict__ Gz2,
+                         const float* __restrict__ r1, const float* __restrict__ r2, const float* __restrict__ dg,
+                         const float* __restrict__ theta, int64_t theta_rs, int H, int64_t R, int64_t D,
+                         float* __restrict__ Zbar, float* __restrict__ theta_bar) {
+  pdl_enter();
+  __shared__ float4 s_t[8][4][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t d = (int64_t)blockIdx.x * 128 + lane * 4;
+  const int64_t row0 = (int64_t)blockIdx.y * 32 + wid * kFin4Rows;
+  const bool dl = d < D;
+  float4 zacc[kFin4Rows], tacc[4];
+#pragma unroll
+  for (int r = 0; r < kFin4Rows; ++r) zacc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int h = 0; h < 4; ++h) tacc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dl) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      if (h < H) {
+        const float* th = theta + h * theta_rs + d;          // rows of theta are D + 1 long: not 16 B aligned
+        const float4 isig = make_float4(expf(-__ldg(th)), expf(-__ldg(th + 1)), expf(-__ldg(th + 2)), expf(-__ldg(th + 3)));
+        float4 z[kFin4Rows], g1[kFin4Rows], g2[kFin4Rows];
+        float rr[kFin4Rows];
+#pragma unroll
+        for (int r = 0; r < kFin4Rows; ++r) {
+          const int64_t row = (int64_t)h * R + row0 + r;
+          const bool ok = row0 + r < R;
+          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+          z[r] = ok ? *reinterpret_cast<const float4*>(zs + row * D + d) : zero;
+          g1[r] = (ok && Gz1) ? *reinterpret_cast<const float4*>(Gz1 + row * D + d) : zero;
+          g2[r] = (ok && Gz2) ? *reinterpret_cast<const float4*>(Gz2 + row * D + d) : zero;
+          rr[r] = ok ? ((r1 ? __ldg(r1 + row) : 0.f) + 2.f * (r2 ? __ldg(r2 + row) : 0.f)) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < kFin4Rows; ++r) {
+          float4 zb;
+          zb.x = fmaf(-rr[r], z[r].x, g1[r].x + 2.f * g2[r].x);
+          zb.y = fmaf(-rr[r], z[r].y, g1[r].y + 2.f * g2[r].y);
+          zb.z = fmaf(-rr[r], z[r].z, g1[r].z + 2.f * g2[r].z);
+          zb.w = fmaf(-rr[r], z[r].w, g1[r].w + 2.f * g2[r].w);
+          zacc[r].x = fmaf(zb.x, isig.x, zacc[r].x); zacc[r].y = fmaf(zb.y, isig.y, zacc[r].y);
+          zacc[r].z = fmaf(zb.z, isig.z, zacc[r].z); zacc[r].w = fmaf(zb.w, isig.w, zacc[r].w);
+          tacc[h].x -= z[r].x * (zb.x + g1[r].x); tacc[h].y -= z[r].y * (zb.y + g1[r].y);
+          tacc[h].z -= z[r].z * (zb.z + g1[r].z); tacc[h].w -= z[r].w * (zb.w + g1[r].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kFin4Rows; ++r)
+      if (row0 + r < R) *reinterpret_cast<float4*>(Zbar + (row0 + r) * D + d) = zacc[r];
+  }
+#pragma unroll
+  for (int h = 0; h < 4; ++h) s_t[wid][h][lane] = tacc[h];
+  __syncthreads();
+  if (wid < H && dl) {                   // warp h sums the 8 partials of hyper sample h
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+      const float4 v = s_t[w8][wid][lane];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float* tb = theta_bar + (int64_t)wid * (D + 1) + d;
+    atomicAdd(tb, a.x); atomicAdd(tb + 1, a.y); atomicAdd(tb + 2, a.z); atomicAdd(tb + 3, a.w);
+  }
+  if (blockIdx.x == 0 && wid >= 4 && wid - 4 < H) {      // gamma part: 2 sum_rows (r1 + r2 + dg), one atomic per (CTA, h)
+    const int h = wid - 4;
+    const int64_t rloc = (int64_t)blockIdx.y * 32 + lane;
+    float v = 0.f;
+    if (rloc < R) {
+      const int64_t row = (int64_t)h * R + rloc;
+      v = (r1 ? r1[row] : 0.f) + (r2 ? r2[row] : 0.f) + (dg ? dg[row] : 0.f);
+    }
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(theta_bar + (int64_t)h * (D + 1) + D, 2.f * v);
+  }
+}
+
 // theta_bar[h][d] += sum_j csum[h][j] xs[h][j][d]^2     grid (D tiles, j tiles, H)
 constexpr int kXsRows = 16;
 __global__ void __launch_bounds__(128)
@@ -276,6 +447,17 @@ extern "C" int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_
   if (dsum && Pa != Pb) return VARGP_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t G = H * C;
+  {   // narrow matrices: warp-per-row kernel (no memset, no row-sum atomics)
+    const bool a16 = ((reinterpret_cast<uintptr_t>(Kbar) | reinterpret_cast<uintptr_t>(K)) % 16 == 0) && Pb % 4 == 0;
+    const int64_t cap = 32 * kRowsK * (a16 ? 4 : 1);
+    if (Pb <= cap && ceil_div(Pa, 32) <= 65535 && G * Pa * Pb <= (int64_t)64 << 20) {
+      dim3 grid((unsigned)ceil_div(Pa, 32), (unsigned)G);
+      const size_t smem = csum ? sizeof(float) * 8 * Pb : 0;
+      if (a16) launch_k((rbf_bwd_prep_rows_kernel<4>), dim3(grid), dim3(256), smem, s, Kbar, K, C, Pa, Pb, rsum, csum, dsum);
+      else launch_k((rbf_bwd_prep_rows_kernel<1>), dim3(grid), dim3(256), smem, s, Kbar, K, C, Pa, Pb, rsum, csum, dsum);
+      return launch_status();
+    }
+  }
   const bool vec4 = Pb % 4 == 0 && Pb >= 2048 &&
                     ((reinterpret_cast<uintptr_t>(Kbar) | reinterpret_cast<uintptr_t>(K)) % 16 == 0);
   const int64_t ctile = kPrepThreads * (vec4 ? 4 : 1);
@@ -302,6 +484,17 @@ extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const flo
   if (!zs || !theta || !Zbar || !theta_bar) return VARGP_ERR_ARG;
   if ((Gz1 != nullptr) != (r1 != nullptr) || (Gz2 != nullptr) != (r2 != nullptr)) return VARGP_ERR_ARG;
   const int64_t R = C * P;
+  {
+    uintptr_t bits = reinterpret_cast<uintptr_t>(zs) | reinterpret_cast<uintptr_t>(Zbar);
+    if (Gz1) bits |= reinterpret_cast<uintptr_t>(Gz1);
+    if (Gz2) bits |= reinterpret_cast<uintptr_t>(Gz2);
+    if (H <= 4 && D % 4 == 0 && bits % 16 == 0 && ceil_div(R, 32) <= 65535) {
+      dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(R, 32));
+      launch_k(rbf_bwd_finish_v4_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs,
+               (int)H, R, D, Zbar, theta_bar);
+      return launch_status();
+    }
+  }
   if (ceil_div(R, kFinRows * kFinChunks) > 65535) return VARGP_ERR_UNSUPPORTED;
   dim3 grid((unsigned)ceil_div(D, kFinThreads), (unsigned)ceil_div(R, kFinRows * kFinChunks));
   launch_k(rbf_bwd_finish_kernel, dim3(grid), dim3(kFinThreads), 0, (cudaStream_t)stream, zs, Gz1, Gz2, r1, r2, dg, theta, theta_rs, H, R,

@@ -110,9 +110,15 @@ class SoftmaxNllFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, f_mean, f_var, y, eps):
     f_mean, f_var = f_mean.detach().contiguous(), f_var.detach().contiguous()
-    nll = torch.zeros((), device=f_mean.device, dtype=f_mean.dtype)
+    ops = _ops()
+    nw = ops.nll_work(eps.shape[0], eps.shape[-1]) if hasattr(ops, 'nll_work') else 0
+    buf = torch.zeros(nw + 1, device=f_mean.device, dtype=f_mean.dtype)      # [workspace | nll]: one fill launch
+    nll = buf[nw]
     gmv = torch.empty((2,) + tuple(f_mean.shape), device=f_mean.device, dtype=f_mean.dtype)
-    _ops().nll_fwd_bwd(f_mean, f_var, eps.contiguous(), y.contiguous(), nll, gmv[0], gmv[1])
+    if nw:
+      ops.nll_fwd_bwd(f_mean, f_var, eps.contiguous(), y.contiguous(), nll, gmv[0], gmv[1], work=buf[:nw])
+    else:
+      ops.nll_fwd_bwd(f_mean, f_var, eps.contiguous(), y.contiguous(), nll, gmv[0], gmv[1])
     ctx.save_for_backward(gmv)
     return nll
 

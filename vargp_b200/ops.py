@@ -78,7 +78,9 @@ def _load():
   lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
-  lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
+  lib.vargp_softmax_nll_work.argtypes = [i64, i64]
+  lib.vargp_softmax_nll_work.restype = i64
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
   lib.vargp_yogi_step.argtypes = [vp, vp, vp, vp, i64] + [ctypes.c_float] * 4 + [vp, vp]
   lib.vargp_hyper_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
@@ -427,13 +429,22 @@ class CudaOps:
                 'sym_phi')
 
   # -- likelihood -----------------------------------------------------------------------------
-  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var):
+  def nll_work(self, H, B):
+    """floats of zero-initialised workspace `nll_fwd_bwd` needs (ticket counter + one partial sum per CTA)."""
+    return int(self.lib.vargp_softmax_nll_work(H, B))
+
+  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var, work=None):
     H, F, C, B = eps_f.shape
     if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous():
       raise VargpError('nll: y must be a contiguous CUDA int64 tensor')
+    if work is None:
+      work = torch.zeros(self.nll_work(H, B), device=f_mean.device, dtype=f_mean.dtype)
+    elif work.numel() < self.nll_work(H, B):
+      raise VargpError('nll: workspace too small')
     self._check(self.lib.vargp_softmax_nll(
       _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), y.data_ptr(), H, F, C, B,
-      _f32(nll, 'nll'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'), self._stream(f_mean)), 'softmax_nll')
+      _f32(nll, 'nll'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'), _f32(work, 'work'), self._stream(f_mean)),
+      'softmax_nll')
 
   def predict(self, f_mean, f_var, eps_f, probs):
     H, F, C, B = eps_f.shape
