@@ -178,13 +178,13 @@ int vargp_rbf_bwd_xside(const float* xs, const float* csum, const float* Gx,
                         float* theta_bar, float* xbar, void* stream);
 
 /* Monte-Carlo softmax likelihood (var_gp/likelihoods.py:13-47), forward and adjoint in one pass:
- * nll += -(1/HF) sum_hfb log softmax_C(f_mean + sqrt(f_var) eps)[y_b];  g_mean, g_var = d nll / d(f_mean, f_var).
+ * nll += -(1/HF) sum_hfb log softmax_C(f_mean + sqrt(f_var) eps)[y_b];  g_mean, g_var = gscale * d nll / d(f_mean, f_var).
  * eps (H,F,C,B); y int64 (B).  The sum is deterministic (per-CTA partial sums combined in a fixed order, no float
  * atomics): `work` holds vargp_softmax_nll_work(H, B) floats; work[0] must be 0 at launch and is 0 again at exit. */
 int64_t vargp_softmax_nll_work(int64_t H, int64_t B);
 int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps, const int64_t* y,
                       int64_t H, int64_t F, int64_t C, int64_t B,
-                      float* nll, float* g_mean, float* g_var, float* work, void* stream);
+                      float* nll, float* g_mean, float* g_var, float gscale, float* work, void* stream);
 /* probs[b][c] = (1/HF) sum_hf softmax_C(f)[c]   (var_gp/likelihoods.py:49-63) */
 int vargp_softmax_predict(const float* f_mean, const float* f_var, const float* eps,
                           int64_t H, int64_t F, int64_t C, int64_t B, float* probs, void* stream);
@@ -199,6 +199,23 @@ int vargp_hyper_fwd(const float* log_mean, const float* log_logvar, const float*
 int vargp_hyper_bwd(const float* log_mean, const float* log_logvar, const float* prior_log_mean,
                     const float* prior_log_logvar, const float* eps, const float* theta_bar, const float* g_kl,
                     int64_t H, int64_t D1, float* log_mean_bar, float* log_logvar_bar, void* stream);
+
+/* Prologue of the fused training step: the current task's parameters into the stacked operands of the step --
+ * Zcat[c][P-M+i][:] = z[c][i][:] (Zcat is (C, P, D)), m_last (C, M) = u_mean, Lu_last (C, M, M) = vec2tril(u_tril_vec)
+ * with a softplus diagonal.  Replaces the torch.cat / vec2tril calls of var_gp/vargp.py:52-59,151-152 (one launch). */
+int vargp_step_assemble(const float* z, const float* u_mean, const float* u_tril_vec, int64_t C, int64_t M, int64_t D,
+                        int64_t P, float* Zcat, float* m_last, float* Lu_last, void* stream);
+/* Epilogue of the fused training step: the adjoints of the stacked operands back into parameter gradients, one launch --
+ * z_grad (C, M, D) = Zbar[:, P-M:, :];  u_mean_grad (C, M) = sum_h mbar[h];  u_tril_vec_grad = adjoint of vec2tril applied
+ * to sum_h Lubar[h] - diag(g_kl_u / Lu_ii) (g_kl_u may be NULL);  log_mean_grad, log_logvar_grad as vargp_hyper_bwd.
+ * mbar (H, C, M) and Lubar (H, C, M, M) are addressed with the hyper-sample strides mbar_hs / Lubar_hs (elements). */
+int vargp_step_grad_finish(const float* Zbar, const float* mbar, int64_t mbar_hs, const float* Lubar, int64_t Lubar_hs,
+                           const float* Lu, const float* u_tril_vec, const float* g_kl_u,
+                           const float* log_mean, const float* log_logvar, const float* prior_log_mean,
+                           const float* prior_log_logvar, const float* eps, const float* theta_bar, const float* g_kl_h,
+                           int64_t H, int64_t C, int64_t M, int64_t D, int64_t P,
+                           float* z_grad, float* u_mean_grad, float* u_tril_vec_grad, float* log_mean_grad,
+                           float* log_logvar_grad, void* stream);
 
 /* Fused Yogi step over a flat parameter buffer (the optimizer the reference trains with,
  * experiments/vargp.py:23): m <- b1 m + (1-b1) g;  v <- v - (1-b2) sign(v - g^2) g^2;

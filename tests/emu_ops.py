@@ -181,3 +181,21 @@ class EmuOps:
     m.mul_(b1).add_(g, alpha=1. - b1)
     v.sub_((1. - b2) * torch.sign(v - g2) * g2)
     p.sub_((lr / bc1) * m / (v.sqrt() / bc2.sqrt() + eps))
+
+  def step_assemble(self, z, u_mean, u_tril_vec, Zcat, m_last, Lu_last):
+    M = z.shape[1]
+    Zcat[:, Zcat.shape[1] - M:] = z
+    m_last.copy_(u_mean.reshape(m_last.shape))
+    self.tril_unpack(u_tril_vec, Lu_last)
+
+  def step_grad_finish(self, Zbar, mbar, Lubar, Lu, u_tril_vec, g_kl_u, log_mean, log_logvar, prior_log_mean, prior_log_logvar,
+                       eps, theta_bar, g_kl_h, z_g, um_g, ut_g, lm_g, llv_g):
+    M = Lu.shape[-1]
+    z_g.copy_(Zbar[:, Zbar.shape[1] - M:])
+    um_g.copy_(mbar.sum(0).reshape(um_g.shape))
+    Lb = Lubar.sum(0)
+    if g_kl_u is not None:
+      Lb = Lb.clone()
+      self.kl_bwd_lu(Lu, g_kl_u[0], Lb)
+    self.tril_unpack_bwd(Lb, u_tril_vec, ut_g)
+    self.hyper_bwd(log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta_bar, g_kl_h[0], lm_g, llv_g)

@@ -335,3 +335,28 @@ def test_likelihood_kernels(cuda_ops, H, F, C, B):
   p = torch.empty(B, C, device='cuda')
   cuda_ops.predict(dev(fm), dev(fv), dev(eps), p)
   assert (p.double().cpu() - p64).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize('H,C,M,S,D', [(3, 10, 60, 5, 784), (2, 3, 7, 1, 37), (1, 4, 9, 2, 2)])
+def test_step_prologue_epilogue_kernels(cuda_ops, H, C, M, S, D):
+  """ops.step_assemble / ops.step_grad_finish (the parameter plumbing of the fused training step) vs their contracts."""
+  P, T = S * M, M * (M + 1) // 2
+  z, um, ut = rnd(C, M, D, seed=1), rnd(C, M, 1, seed=2), rnd(C, T, seed=3)
+  Zc64, ml64, Ll64 = rnd(C, P, D, seed=4), torch.empty(C, M, dtype=torch.float64), torch.empty(C, M, M, dtype=torch.float64)
+  Zc, ml, Ll = dev(Zc64), torch.empty(C, M, device='cuda'), torch.empty(C, M, M, device='cuda')
+  EMU.step_assemble(z, um, ut, Zc64, ml64, Ll64)
+  cuda_ops.step_assemble(dev(z), dev(um), dev(ut), Zc, ml, Ll)
+  close(Zc, Zc64, 1e-7, 'Zcat'); close(ml, ml64, 1e-7, 'm_last'); close(Ll, Ll64, 1e-6, 'Lu_last')
+  Zb, mb, Lb = rnd(C, P, D, seed=5), rnd(H, C, M, 1, seed=6), rnd(H, C, M, M, seed=7)
+  lm, llv, pm, plv = (rnd(D + 1, seed=8 + i, scale=0.3) for i in range(4))
+  eps, thb = rnd(H, D + 1, seed=12), rnd(H, D + 1, seed=13)
+  gu, gh = torch.tensor([0.7], dtype=torch.float64), torch.tensor([1.3], dtype=torch.float64)
+  for use_gu in (True, False):
+    outs64 = [torch.empty(C, M, D, dtype=torch.float64), torch.empty(C, M, 1, dtype=torch.float64),
+              torch.empty(C, T, dtype=torch.float64), torch.empty(D + 1, dtype=torch.float64), torch.empty(D + 1, dtype=torch.float64)]
+    outs = [torch.full(o.shape, float('nan'), device='cuda') for o in outs64]
+    EMU.step_grad_finish(Zb, mb, Lb, Ll64, ut, gu if use_gu else None, lm, llv, pm, plv, eps, thb, gh, *outs64)
+    cuda_ops.step_grad_finish(dev(Zb), dev(mb), dev(Lb), Ll, dev(ut), dev(gu) if use_gu else None, dev(lm), dev(llv), dev(pm),
+                              dev(plv), dev(eps), dev(thb), dev(gh), *outs)
+    for a, b, nm in zip(outs, outs64, ('z_g', 'um_g', 'ut_g', 'lm_g', 'llv_g')):
+      close(a, b, 1e-5, nm)

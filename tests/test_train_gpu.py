@@ -159,3 +159,36 @@ def test_stepper_reports_non_pd_after_the_step(cuda_ops):
     st.check_errors()
   with pytest.raises(torch.linalg.LinAlgError):
     gp.predict(x)
+
+
+@pytest.mark.parametrize('t', [0, 2])
+def test_fused_step_matches_autograd_step(cuda_ops, t):
+  """fused_step.FusedElbo (tape-free value-and-gradient, gradients written straight into the flat Yogi buffer) vs
+  VARGP.loss + autograd through the same kernels: same seed -> same loss terms and gradients, and after a few Yogi steps
+  the same parameters."""
+  from vargp_b200.train import ElboStepper
+  from vargp_b200.synthetic import make_case
+  out = {}
+  for fused in (False, True):
+    params, prev, x, y, _ = make_case(C=10, D=784, M=20, t=t, B=256, sigma=10., seed=3)
+    gp = util.build_model(params, prev, 3, 10, {}, 'cuda', torch.float32)
+    st = ElboStepper(gp, n_data=2560, batch_size=256, beta=1.7, lr=1e-2, use_graph=False, fused=fused)
+    assert (st.fused is not None) == fused
+    torch.manual_seed(7)
+    st._load_inputs(x.cuda(), y.cuda())
+    st._grad_body()
+    torch.cuda.synchronize()
+    g1, t1 = st.opt.flat_g.clone(), st.terms_vec.clone()
+    torch.manual_seed(7)
+    for i in range(4):
+      st.step(x.cuda(), y.cuda())
+    st.check_errors()
+    out[fused] = (g1, t1, st.opt.flat_p.clone(), st.terms_vec.clone())
+  assert torch.equal(out[True][1], out[False][1])                 # forward: same kernels, deterministic reductions
+  assert util.relerr(out[True][0], out[False][0]) < 1e-5
+  # per parameter (the flat buffer is dominated by z)
+  for k, (a, b) in enumerate(zip(out[True][0].split([10 * 20 * 784, 200, 10 * 210, 785, 785]),
+                                 out[False][0].split([10 * 20 * 784, 200, 10 * 210, 785, 785]))):
+    assert util.relerr(a, b) < 1e-5, k
+  assert util.relerr(out[True][2], out[False][2]) < 1e-5
+  assert util.relerr(out[True][3], out[False][3]) < 1e-5

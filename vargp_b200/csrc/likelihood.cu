@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(128)
 softmax_nll_kernel(const float* __restrict__ f_mean, const float* __restrict__ f_var,
                    const float* __restrict__ eps, const int64_t* __restrict__ y,
                    int64_t H, int64_t F, int64_t C, int64_t B,
-                   float* __restrict__ nll, float* __restrict__ g_mean, float* __restrict__ g_var,
+                   float* __restrict__ nll, float* __restrict__ g_mean, float* __restrict__ g_var, float gscale,
                    float* __restrict__ work) {
   pdl_enter();
   __shared__ float scratch[32];
@@ -65,8 +65,8 @@ softmax_nll_kernel(const float* __restrict__ f_mean, const float* __restrict__ f
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
       if (c < C) {
-        g_mean[(h * C + c) * B + b] = gm[c] * scale;
-        g_var[(h * C + c) * B + b] = gs[c] * scale / (2.f * sd[c]);
+        g_mean[(h * C + c) * B + b] = gm[c] * (scale * gscale);
+        g_var[(h * C + c) * B + b] = gs[c] * (scale * gscale) / (2.f * sd[c]);
       }
     }
     acc *= scale;
@@ -152,17 +152,17 @@ extern "C" int64_t vargp_softmax_nll_work(int64_t H, int64_t B) { return 1 + H *
 
 extern "C" int vargp_softmax_nll(const float* f_mean, const float* f_var, const float* eps, const int64_t* y,
                                  int64_t H, int64_t F, int64_t C, int64_t B, float* nll, float* g_mean,
-                                 float* g_var, float* work, void* stream) {
+                                 float* g_var, float gscale, float* work, void* stream) {
   if (!f_mean || !f_var || !eps || !y || !nll || !g_mean || !g_var || !work) return VARGP_ERR_ARG;
   if (H < 1 || F < 1 || C < 1 || B < 0) return VARGP_ERR_ARG;
   if (C > 32 || H > 65535) return VARGP_ERR_UNSUPPORTED;
   if (B == 0) return 0;
   dim3 grid((unsigned)ceil_div(B, 128), (unsigned)H);
   cudaStream_t s = (cudaStream_t)stream;
-  if (C <= 4) launch_k((softmax_nll_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
-  else if (C <= 10) launch_k((softmax_nll_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
-  else if (C <= 16) launch_k((softmax_nll_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
-  else launch_k((softmax_nll_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, work);
+  if (C <= 4) launch_k((softmax_nll_kernel<4>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, gscale, work);
+  else if (C <= 10) launch_k((softmax_nll_kernel<10>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, gscale, work);
+  else if (C <= 16) launch_k((softmax_nll_kernel<16>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, gscale, work);
+  else launch_k((softmax_nll_kernel<32>), dim3(grid), dim3(128), 0, s, f_mean, f_var, eps, y, H, F, C, B, nll, g_mean, g_var, gscale, work);
   return launch_status();
 }
 

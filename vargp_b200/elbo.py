@@ -188,11 +188,13 @@ def _pairs(G, P, *tail, dev, dt, slots, zero=False):
   return full, full[:G]
 
 
-def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=None):
+def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=None, zeroed=None):
   """theta (H, D+1); Zcat (C, P, D); x (B, D); m_all (S, C, M); Lu_all (S, C, M, M) lower.
 
   Returns f_mean, f_var (H, C, B), kl_u (0-d tensor or None) and fills ``ctx`` for the backward.
   With `shard` (a FactorShard) the factor stage only runs for this rank's (h, c) pairs, see FactorShard.
+  `zeroed` = (info int32 (H*C,), kl 0-d): caller-provided, already zero-filled status words / KL accumulator (the fused
+  training step carves them out of its per-step arena instead of paying a fill launch here).
   """
   ops = _ops()
   H, D1 = theta.shape
@@ -249,7 +251,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   # V_SIDE: only when one rectangle covers every pair (unsharded), so that W is complete after its chol_inv
   v_early = V_SIDE and shard is None and len(rects) == 1
   V_early = new(H, C, P, B) if v_early else None
-  if dt == torch.float32:       # Cholesky status words and the KL accumulator share one zero-filled buffer
+  if zeroed is not None:
+    info, kl0 = zeroed
+  elif dt == torch.float32:     # Cholesky status words and the KL accumulator share one zero-filled buffer
     zb = torch.zeros(G + 1, device=dev, dtype=dt)
     info, kl0 = zb[:G].view(torch.int32), zb[G]
   else:
@@ -312,11 +316,15 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   return f_mean, f_var, kl, info, L
 
 
-def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
+def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=False):
   """Adjoint of `marginal_forward`.  g_mean, g_var (H, C, B) or None; g_kl 0-d tensor or None.
 
   Returns grads (theta (H, D+1), Zcat (C, P, D), x (B, D) or None, m_all (S, C, M), Lu_all (S, C, M, M)); with a
   FactorShard these are the rank's partial sums.
+  `last_raw` (fused training step: the previous tasks' variational parameters are constants): only the current task's
+  block of the whitening adjoint is formed and the last two results are the per-hyper-sample terms mbar (H, C, M, 1),
+  Lubar (H, C, M, M) of that block, WITHOUT the sum over h and without the -g_kl / Lu_ii term of the KL (both are
+  folded into ops.step_grad_finish).
   """
   ops = _ops()
   H, C, P, B, D, S, M = ctx.dims
@@ -372,8 +380,9 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
   # factor-stage adjoint on this rank's (h, c) rectangles; whatever is not owned stays zero
   sharded = shard is not None
   mk = torch.zeros if sharded else torch.empty
-  Lubar_h = mk(H, S, C, M, M, device=dev, dtype=dt)             # task-major: the sum over h is in parameter layout
-  mbar_h = mk(H, S, C, M, 1, device=dev, dtype=dt)
+  Sg = 1 if last_raw else S                                     # task blocks whose parameter gradients are formed
+  Lubar_h = mk(H, Sg, C, M, M, device=dev, dtype=dt)            # task-major: the sum over h is in parameter layout
+  mbar_h = mk(H, Sg, C, M, 1, device=dev, dtype=dt)
   Gz2, r2, dg = mk(H, C, P, D, device=dev, dtype=dt), mk(H, C, P, device=dev, dtype=dt), mk(H, C, P, device=dev, dtype=dt)
   X, Y = new(H, C, P, P), new(H, C, P, P)
   g_kl_r = None
@@ -402,10 +411,11 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     ops.gemm(Tbar[r], LuB[:, c0:c1].transpose(-1, -2), Wbd, beta=1., a_tri='lower', b_tri='upper', c_tri='lower',
              tag='whiten_adj', zeroed=True)
     ops.gemm(nub5, mB[:, c0:c1].unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
-    ops.gemm(Wd.transpose(-1, -2), Tbar[r], Lubar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4), a_tri='upper',
-             b_tri='lower', c_tri='lower', tag='whiten_adj', zeroed=True)
-    ops.gemm(Wd.transpose(-1, -2), nub5, mbar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4), a_tri='upper',
-             tag='whiten_adj', zeroed=True)
+    s0 = S - Sg
+    ops.gemm(Wd[:, :, s0:].transpose(-1, -2), Tbar[r][:, :, s0:], Lubar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
+             a_tri='upper', b_tri='lower', c_tri='lower', tag='whiten_adj', zeroed=True)
+    ops.gemm(Wd[:, :, s0:].transpose(-1, -2), nub5[:, :, s0:], mbar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
+             a_tri='upper', tag='whiten_adj', zeroed=True)
     # Cholesky-inverse adjoint:  Kbar = -W^T Xi W,  Xi = (Phi(X) + Phi(X)^T)/2,  X = tril(Wbar W^T)
     ops.gemm(Wbar[r], W[r].transpose(-1, -2), X[r], a_tri='lower', b_tri='upper', c_tri='lower', tag='X=Wbar*Wt',
              zeroed=True)
@@ -416,11 +426,14 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False):
     # RBF adjoint of the Kzz side                                                
     ops.rbf_bwd_prep(Kzzbar, Kzz[r], r2[r], None, dg[r])          # Kzzbar <- Kzzbar * Kzz (diag -> dg) ; row sums
     ops.gemm(Kzzbar, zs[r], Gz2[r], tag='Gz2=Wk2*zs')
-  Lu_bar = Lubar_h.sum(0)                                        # (S, C, M, M)
-  m_bar = mbar_h.sum(0).squeeze(-1)                              # (S, C, M)
-  if g_kl is not None and (not sharded or shard.rank == 0):
-    # d/dLu_t of -sum_i log Lu_t,ii  (mean over h of H identical terms; counted once across the ranks)
-    ops.kl_bwd_lu(Lu_all[S - 1], g_kl, Lu_bar[S - 1])
+  if last_raw:
+    m_bar, Lu_bar = mbar_h[:, 0], Lubar_h[:, 0]                  # (H, C, M, 1), (H, C, M, M)
+  else:
+    Lu_bar = Lubar_h.sum(0)                                      # (S, C, M, M)
+    m_bar = mbar_h.sum(0).squeeze(-1)                            # (S, C, M)
+    if g_kl is not None and (not sharded or shard.rank == 0):
+      # d/dLu_t of -sum_i log Lu_t,ii  (mean over h of H identical terms; counted once across the ranks)
+      ops.kl_bwd_lu(Lu_all[S - 1], g_kl, Lu_bar[S - 1])
 
   Z_bar = new(C, P, D)
   fork.join()

@@ -78,7 +78,9 @@ def _load():
   lib.vargp_rbf_bwd_prep.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
-  lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
+  lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, ctypes.c_float, vp, vp]
+  lib.vargp_step_assemble.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+  lib.vargp_step_grad_finish.argtypes = [vp, vp, i64, vp, i64] + [vp] * 10 + [i64] * 5 + [vp] * 6
   lib.vargp_softmax_nll_work.argtypes = [i64, i64]
   lib.vargp_softmax_nll_work.restype = i64
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
@@ -433,7 +435,7 @@ class CudaOps:
     """floats of zero-initialised workspace `nll_fwd_bwd` needs (ticket counter + one partial sum per CTA)."""
     return int(self.lib.vargp_softmax_nll_work(H, B))
 
-  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var, work=None):
+  def nll_fwd_bwd(self, f_mean, f_var, eps_f, y, nll, g_mean, g_var, work=None, gscale=1.0):
     H, F, C, B = eps_f.shape
     if y.dtype != torch.int64 or not y.is_cuda or not y.is_contiguous():
       raise VargpError('nll: y must be a contiguous CUDA int64 tensor')
@@ -443,7 +445,8 @@ class CudaOps:
       raise VargpError('nll: workspace too small')
     self._check(self.lib.vargp_softmax_nll(
       _f32(f_mean, 'f_mean'), _f32(f_var, 'f_var'), _f32(eps_f, 'eps_f'), y.data_ptr(), H, F, C, B,
-      _f32(nll, 'nll'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'), _f32(work, 'work'), self._stream(f_mean)),
+      _f32(nll, 'nll'), _f32(g_mean, 'g_mean'), _f32(g_var, 'g_var'), float(gscale), _f32(work, 'work'),
+      self._stream(f_mean)),
       'softmax_nll')
 
   def predict(self, f_mean, f_var, eps_f, probs):
@@ -470,6 +473,31 @@ class CudaOps:
                                          None if theta_bar is None else _f32(theta_bar, 'theta_bar'),
                                          None if g_kl is None else _f32(g_kl, 'g_kl'), H, D1,
                                          _f32(m_bar, 'm_bar'), _f32(lv_bar, 'lv_bar'), self._stream(m_bar)), 'hyper_bwd')
+
+  # -- fused training step: parameter plumbing ------------------------------------------------
+  def step_assemble(self, z, u_mean, u_tril_vec, Zcat, m_last, Lu_last):
+    C, M, D = z.shape
+    P = Zcat.shape[1]
+    self._check(self.lib.vargp_step_assemble(_f32(z, 'z'), _f32(u_mean, 'u_mean'), _f32(u_tril_vec, 'u_tril_vec'), C, M, D, P,
+                                             _f32(Zcat, 'Zcat'), _f32(m_last, 'm_last'), _f32(Lu_last, 'Lu_last'),
+                                             self._stream(z)), 'step_assemble')
+
+  def step_grad_finish(self, Zbar, mbar, Lubar, Lu, u_tril_vec, g_kl_u, log_mean, log_logvar, prior_log_mean, prior_log_logvar,
+                       eps, theta_bar, g_kl_h, z_g, um_g, ut_g, lm_g, llv_g):
+    """mbar (H, C, M[, 1]) / Lubar (H, C, M, M): views whose trailing dims are contiguous (any stride along h)."""
+    C, P, D = Zbar.shape
+    H, M = Lubar.shape[0], Lubar.shape[-1]
+    for t, nm in ((mbar, 'mbar'), (Lubar, 'Lubar')):
+      _f32(t, nm, contiguous=False)
+      if not t[0].is_contiguous():
+        raise VargpError(f'step_grad_finish: {nm}[h] must be contiguous')
+    self._check(self.lib.vargp_step_grad_finish(
+      _f32(Zbar, 'Zbar'), mbar.data_ptr(), mbar.stride(0), Lubar.data_ptr(), Lubar.stride(0), _f32(Lu, 'Lu'),
+      _f32(u_tril_vec, 'u_tril_vec'), None if g_kl_u is None else _f32(g_kl_u, 'g_kl_u'), _f32(log_mean, 'log_mean'),
+      _f32(log_logvar, 'log_logvar'), _f32(prior_log_mean, 'prior_log_mean'), _f32(prior_log_logvar, 'prior_log_logvar'),
+      _f32(eps, 'eps'), _f32(theta_bar, 'theta_bar'), _f32(g_kl_h, 'g_kl_h'), H, C, M, D, P,
+      _f32(z_g, 'z_g'), _f32(um_g, 'um_g'), _f32(ut_g, 'ut_g'), _f32(lm_g, 'lm_g'), _f32(llv_g, 'llv_g'),
+      self._stream(Zbar)), 'step_grad_finish')
 
   # -- optimizer ------------------------------------------------------------------------------
   def yogi_step(self, p, g, m, v, lr, b1, b2, eps, pows):

@@ -19,14 +19,17 @@ from .optim import FlatYogi
 
 USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
 GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'
+FUSED_STEP = os.environ.get('VARGP_FUSED_STEP', '1') != '0'
 
 
 class ElboStepper:
   def __init__(self, gp, n_data, batch_size, beta=1.0, lr=1e-2, world_size=1, use_graph=True, optimizer=None,
-               shard_factor=None):
+               shard_factor=None, fused=None):
     """shard_factor: also shard the replicated O(P^3) factor stage over the ranks (elbo.FactorShard); default: on
     when world_size > 1 and the task has at least 512 inducing points per class (below that the three extra
-    collectives cost more than the replicated work)."""
+    collectives cost more than the replicated work).
+    fused: take the tape-free value-and-gradient path of `fused_step.FusedElbo` (default: whenever the model is
+    eligible -- plain RBF kernel, sampled hypers, ep_var_mean=True); False keeps loss() + autograd."""
     self.gp, self.n_data, self.beta, self.world = gp, n_data, beta, world_size
     self.global_batch = batch_size * world_size
     self.opt = optimizer or FlatYogi(gp.parameters(), lr=lr)
@@ -56,12 +59,20 @@ class ElboStepper:
     self.terms_vec = None        # (kl_hypers, kl_u, nll) of the last step as one (3,) device tensor
     self._pf = None              # prefetch state: (x_src, y_src, x_staging, y_staging, ready event)
     self._copy_stream = None
+    from . import fused_step
+    if fused is None:
+      fused = FUSED_STEP
+    self.fused = fused_step.FusedElbo(gp, self.coef, self.shard) if (fused and fused_step.eligible(gp)) else None
     self.info = None             # Cholesky status words of the last step (the graph's static buffer in graph mode)
     self._host_terms = None      # pinned (2, 3) ring of the loss terms fetched by `fetch_terms_async`
     self._host_ev = [None, None]
     self._host_n = 0
 
   def _grad_body(self):
+    if self.fused is not None:           # tape-free path: every gradient is overwritten in place, nothing to zero
+      self.terms_vec = tv = self.fused.value_and_grad(self.x, self.y)
+      self.info = self.gp._last_info
+      return (tv[0], tv[1], tv[2])
     self.opt.zero_grad()
     gp = self.gp
     sync, gp.sync_errors, gp.factor_shard = gp.sync_errors, False, self.shard   # no host sync inside the step ...
