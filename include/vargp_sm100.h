@@ -139,6 +139,27 @@ int vargp_kl_bwd(const float* W, const float* T, const float* nu, const float* g
                  int64_t H, int64_t C, int64_t P, int64_t M, float* Wbar, float* Tbar, float* nubar, void* stream);
 int vargp_kl_bwd_lu(const float* Lu, const float* g_kl, int64_t C, int64_t M, float* Lubar, void* stream);
 
+/* Whitening of the variational parameters on the M x M diagonal task blocks, forward and adjoint, one shared-memory
+ * kernel each (whiten.cu) for the (h, c) pairs of the rectangle [h0, h1) x [c0, c1):
+ *   forward:  T_s = W_ss Lu_s, nu_s = W_ss m_s, N_ss += T_s T_s^T (N must already hold jitter W W^T) and, with kl != NULL,
+ *             kl += (1/H) sum_hc KL_hc (same value as vargp_kl_fwd; deterministic).  `work`: vargp_whiten_fwd_work(H, C)
+ *             floats, work[0] == 0 at launch and again at exit.
+ *   adjoint:  k = g_kl / H on the last block (g_kl may be NULL), else 0;  Tbar_s = tril(2 G_ss T_s) + k T_s;
+ *             nubar'_s = nubar_s + k nu_s;  Wbar_ss += tril(Tbar_s Lu_s^T + nubar'_s m_s^T) - k diag(1 / W_ii);  for the
+ *             blocks s >= s_grad0:  Lubar[h][s - s_grad0][c] = tril(W_ss^T Tbar_s),  mbar[h][s - s_grad0][c] = W_ss^T nubar'_s.
+ * W, N, G, Wbar (H, C, P, P); T (H, C, S, M, M); nu, nubar (H, C, P); Lu_all (S, C, M, M); m_all (S, C, M);
+ * Lubar (H, S - s_grad0, C, M, M); mbar (H, S - s_grad0, C, M).  Returns -2 for M > vargp_whiten_max_m(adjoint).
+ * Replaces the block-diagonal part of var_gp/vargp.py:35-88 (compute_q) and the KL of vargp.py:182-190. */
+int64_t vargp_whiten_fwd_work(int64_t H, int64_t C);
+int64_t vargp_whiten_max_m(int adjoint);
+int vargp_whiten_fwd(const float* W, const float* Lu_all, const float* m_all, int64_t H, int64_t C, int64_t S, int64_t M,
+                     int64_t P, int64_t h0, int64_t h1, int64_t c0, int64_t c1, float* T, float* nu, float* N, float* kl,
+                     float* work, void* stream);
+int vargp_whiten_bwd(const float* W, const float* T, const float* nu, const float* Lu_all, const float* m_all,
+                     const float* G, const float* nubar, const float* g_kl, int64_t H, int64_t C, int64_t S, int64_t M,
+                     int64_t P, int64_t h0, int64_t h1, int64_t c0, int64_t c1, int64_t s_grad0, float* Wbar, float* Lubar,
+                     float* mbar, void* stream);
+
 /* Predictive marginal (var_gp/gp_utils.py:178-186) from V = W Kzx and NV = N V, where
  * N = blockdiag(T_s T_s^T) + jitter W W^T (P x P, symmetric) collects everything quadratic in V:
  *   f_mean[g][b] = sum_p nu[g][p] V[g][p][b];

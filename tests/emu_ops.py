@@ -199,3 +199,43 @@ class EmuOps:
       self.kl_bwd_lu(Lu, g_kl_u[0], Lb)
     self.tril_unpack_bwd(Lb, u_tril_vec, ut_g)
     self.hyper_bwd(log_mean, log_logvar, prior_log_mean, prior_log_logvar, eps, theta_bar, g_kl_h[0], lm_g, llv_g)
+
+  # -- whitening on the diagonal task blocks (contracts of whiten.cu) --
+  def whiten_max_m(self, adjoint):
+    return 96 if adjoint else 128
+
+  def whiten_fwd(self, W, Lu_all, m_all, T, nu, N, kl, rect=None, work=None):
+    H, C, P, _ = W.shape
+    S, M = Lu_all.shape[0], Lu_all.shape[-1]
+    h0, h1, c0, c1 = rect or (0, H, 0, C)
+    for s in range(S):
+      sl = slice(s * M, (s + 1) * M)
+      Wss = W[h0:h1, c0:c1, sl, sl]
+      Ts = Wss @ Lu_all[s, c0:c1]
+      T[h0:h1, c0:c1, s] = Ts
+      nu[h0:h1, c0:c1, sl] = (Wss @ m_all[s, c0:c1].unsqueeze(-1)).squeeze(-1)
+      N[h0:h1, c0:c1, sl, sl] += Ts @ Ts.transpose(-1, -2)
+    if kl is not None:
+      wd = W[h0:h1, c0:c1].diagonal(dim1=-2, dim2=-1)[..., P - M:]
+      val = -wd.log().sum() - (h1 - h0) * Lu_all[S - 1, c0:c1].diagonal(dim1=-2, dim2=-1).log().sum() \
+            + 0.5 * ((T[h0:h1, c0:c1, -1] ** 2).sum() + (nu[h0:h1, c0:c1, P - M:] ** 2).sum() - M * (h1 - h0) * (c1 - c0))
+      kl.add_(val / H)
+
+  def whiten_bwd(self, W, T, nu, Lu_all, m_all, G, nubar, g_kl, Wbar, Lubar, mbar, s_grad0=0, rect=None):
+    H, C, P, _ = W.shape
+    S, M = Lu_all.shape[0], Lu_all.shape[-1]
+    h0, h1, c0, c1 = rect or (0, H, 0, C)
+    mb = mbar.view(H, S - s_grad0, C, M)
+    for s in range(S):
+      sl = slice(s * M, (s + 1) * M)
+      k = (g_kl.reshape(-1)[0] / H) if (g_kl is not None and s == S - 1) else 0.
+      Ts, Wss = T[h0:h1, c0:c1, s], W[h0:h1, c0:c1, sl, sl]
+      Tb = torch.tril(2. * G[h0:h1, c0:c1, sl, sl] @ Ts) + k * Ts
+      nb = nubar[h0:h1, c0:c1, sl] + k * nu[h0:h1, c0:c1, sl]
+      upd = torch.tril(Tb @ Lu_all[s, c0:c1].transpose(-1, -2) + nb.unsqueeze(-1) * m_all[s, c0:c1].unsqueeze(-2))
+      if g_kl is not None and s == S - 1:
+        upd = upd - torch.diag_embed(k / Wss.diagonal(dim1=-2, dim2=-1))
+      Wbar[h0:h1, c0:c1, sl, sl] += upd
+      if s >= s_grad0:
+        Lubar[h0:h1, s - s_grad0, c0:c1] = torch.tril(Wss.transpose(-1, -2) @ Tb)
+        mb[h0:h1, s - s_grad0, c0:c1] = (Wss.transpose(-1, -2) @ nb.unsqueeze(-1)).squeeze(-1)

@@ -360,3 +360,37 @@ def test_step_prologue_epilogue_kernels(cuda_ops, H, C, M, S, D):
                               dev(plv), dev(eps), dev(thb), dev(gh), *outs)
     for a, b, nm in zip(outs, outs64, ('z_g', 'um_g', 'ut_g', 'lm_g', 'llv_g')):
       close(a, b, 1e-5, nm)
+
+
+@pytest.mark.parametrize('H,C,S,M,rect', [(3, 10, 5, 60, None), (2, 3, 1, 7, None), (1, 4, 2, 9, None), (2, 2, 2, 96, None),
+                                          (3, 4, 3, 33, (1, 2, 1, 4)), (2, 5, 2, 64, (0, 2, 2, 5)), (1, 2, 1, 128, None)])
+def test_whiten_block_kernels(cuda_ops, H, C, S, M, rect):
+  """whiten.cu (T, nu, N += T T^T, KL forward; Tbar / KL adjoint / whitening adjoint backward on the M x M task blocks in one
+  shared-memory kernel each) vs the contracts in tests/emu_ops.py, incl. (h, c) sub-rectangles (factor sharding)."""
+  P = S * M
+  W = (rnd(H, C, P, P, seed=1, scale=0.1).tril() + torch.eye(P, dtype=torch.float64))
+  Lu = rnd(S, C, M, M, seed=2, scale=0.2).tril() + torch.eye(M, dtype=torch.float64)
+  m = rnd(S, C, M, seed=3)
+  N0 = rnd(H, C, P, P, seed=4)
+  T64, nu64, N64, kl64 = torch.zeros(H, C, S, M, M, dtype=torch.float64), torch.zeros(H, C, P, dtype=torch.float64), N0.clone(), \
+      torch.zeros((), dtype=torch.float64)
+  EMU.whiten_fwd(W, Lu, m, T64, nu64, N64, kl64, rect=rect)
+  T, nu, N, kl = torch.zeros(H, C, S, M, M, device='cuda'), torch.zeros(H, C, P, device='cuda'), dev(N0), torch.zeros((), device='cuda')
+  for rep in range(2):            # twice: the ticket workspace must come back zeroed
+    cuda_ops.whiten_fwd(dev(W), dev(Lu), dev(m), T, nu, N, kl, rect=rect)
+    if rep == 0:
+      N.copy_(dev(N0)); kl.zero_()
+  close(T, T64, 1e-6, 'T'); close(nu, nu64, 1e-6, 'nu'); close(N, N64, 1e-6, 'N'); close(kl, kl64, 1e-5, 'kl')
+  if M > 96:
+    return
+  G = rnd(H, C, P, P, seed=5); G = G + G.transpose(-1, -2)
+  nubar, Wb0 = rnd(H, C, P, seed=6), rnd(H, C, P, P, seed=7)
+  g_kl = torch.tensor([0.7], dtype=torch.float64)
+  for s0, use_kl in ((0, True), (S - 1, True), (0, False)):
+    Sg = S - s0
+    Wb64, Lb64, mb64 = Wb0.clone(), torch.zeros(H, Sg, C, M, M, dtype=torch.float64), torch.zeros(H, Sg, C, M, 1, dtype=torch.float64)
+    EMU.whiten_bwd(W, T64, nu64, Lu, m, G, nubar, g_kl if use_kl else None, Wb64, Lb64, mb64, s_grad0=s0, rect=rect)
+    Wb, Lb, mb = dev(Wb0), torch.zeros(H, Sg, C, M, M, device='cuda'), torch.zeros(H, Sg, C, M, 1, device='cuda')
+    cuda_ops.whiten_bwd(dev(W), dev(T64), dev(nu64), dev(Lu), dev(m), dev(G), dev(nubar), dev(g_kl) if use_kl else None, Wb, Lb, mb,
+                        s_grad0=s0, rect=rect)
+    close(Wb, Wb64, 1e-6, 'Wbar'); close(Lb, Lb64, 1e-6, 'Lubar'); close(mb, mb64, 1e-6, 'mbar')

@@ -51,6 +51,8 @@ KZZ_FIRST = os.environ.get('VARGP_KZZ_FIRST', '1') != '0'
 #                          factorisation), so that it overlaps the T / nu / KL / N chain instead of following it.
 STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '1') != '0'
 V_SIDE = os.environ.get('VARGP_V_SIDE', '1') != '0'
+# VARGP_WHITEN=0: the per-task-block products through the batched GEMMs even when M fits the shared-memory kernels
+USE_WHITEN = os.environ.get('VARGP_WHITEN', '1') != '0'
 
 
 class _Fork:
@@ -193,8 +195,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
 
   Returns f_mean, f_var (H, C, B), kl_u (0-d tensor or None) and fills ``ctx`` for the backward.
   With `shard` (a FactorShard) the factor stage only runs for this rank's (h, c) pairs, see FactorShard.
-  `zeroed` = (info int32 (H*C,), kl 0-d): caller-provided, already zero-filled status words / KL accumulator (the fused
-  training step carves them out of its per-step arena instead of paying a fill launch here).
+  `zeroed` = (info int32 (H*C,), kl 0-d, whiten workspace (1 + H*C,)): caller-provided, already zero-filled status
+  words / KL accumulator / ticket workspace (the fused training step carves them out of its per-step arena instead of
+  paying fill launches here).
   """
   ops = _ops()
   H, D1 = theta.shape
@@ -251,8 +254,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   # V_SIDE: only when one rectangle covers every pair (unsharded), so that W is complete after its chol_inv
   v_early = V_SIDE and shard is None and len(rects) == 1
   V_early = new(H, C, P, B) if v_early else None
+  wwork = None
   if zeroed is not None:
-    info, kl0 = zeroed
+    info, kl0, wwork = zeroed
   elif dt == torch.float32:     # Cholesky status words and the KL accumulator share one zero-filled buffer
     zb = torch.zeros(G + 1, device=dev, dtype=dt)
     info, kl0 = zb[:G].view(torch.int32), zb[G]
@@ -261,6 +265,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   kl = kl0 if want_kl else None
   LuB = Lu_all.permute(1, 0, 2, 3).unsqueeze(0)                 # (1, C, S, M, M), broadcast over h
   mB = m_all.permute(1, 0, 2).unsqueeze(0).unsqueeze(-1)        # (1, C, S, M, 1)
+  use_wf = USE_WHITEN and hasattr(ops, 'whiten_fwd') and M <= ops.whiten_max_m(False)
   for (h0, h1, c0, c1) in rects:
     r = (slice(h0, h1), slice(c0, c1))
     th, Hs, Cs = theta[h0:h1], h1 - h0, c1 - c0
@@ -275,6 +280,13 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
       fork.after_main()                        # W is complete
       with fork:
         ops.gemm(W, Kzx, V_early, a_tri='lower', tag='V=W*Kzx', zeroed=True)
+    if use_wf:
+      # small task blocks: N = eps W W^T by GEMM, then ONE shared-memory kernel for T_s = W_ss Lu_s, nu_s = W_ss m_s,
+      # N_ss += T_s T_s^T and the KL (whiten.cu) instead of four launches on 128 x 128 tiles that are 95 % padding
+      ops.gemm(W[r], W[r].transpose(-1, -2), N[r], alpha=JITTER, a_tri='lower', b_tri='upper', tag='N=eps*W*Wt',
+               zeroed=True)
+      ops.whiten_fwd(W, Lu_all, m_all, T, nu, N, kl if want_kl else None, rect=(h0, h1, c0, c1), work=wwork)
+      continue
     # whitened variational parameters (block diagonal)
     Wd = _blocks(W[r], S, M)
     ops.gemm(Wd, LuB[:, c0:c1], T[r], a_tri='lower', b_tri='lower', tag='T=Wss*Lu', zeroed=True)
@@ -386,36 +398,47 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
   Gz2, r2, dg = mk(H, C, P, D, device=dev, dtype=dt), mk(H, C, P, device=dev, dtype=dt), mk(H, C, P, device=dev, dtype=dt)
   X, Y = new(H, C, P, P), new(H, C, P, P)
   g_kl_r = None
+  use_wb = USE_WHITEN and hasattr(ops, 'whiten_bwd') and M <= ops.whiten_max_m(True)
   for (h0, h1, c0, c1) in rects:
     r = (slice(h0, h1), slice(c0, c1))
     Hs, Cs = h1 - h0, c1 - c0
     if have_data:
       ops.sym_phi(Gm[r], mirror=True)
-      # N = blockdiag(T_s T_s^T) + eps W W^T  =>  Tbar_s = tril(2 G_ss T_s),  Wbar += tril(2 eps G W)
-      ops.gemm(_blocks(Gm[r], S, M), T[r], Tbar[r], alpha=2., b_tri='lower', c_tri='lower', tag='Tbar=2*Gss*T',
-               zeroed=True)
-      ops.gemm(Gm[r], W[r], Wbar[r], alpha=2. * JITTER, beta=1., b_tri='lower', c_tri='lower', tag='Wbar+=2eps*G*W',
-               zeroed=True)
-    if g_kl is not None:
-      # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block (the kernel divides by ITS H)
-      if Hs == H:
-        g_here = g_kl
-      else:
-        if g_kl_r is None:
-          g_kl_r = g_kl * (1.0 / H)
-        g_here = g_kl_r
-      ops.kl_bwd(W[r], T[r], nu[r], M, g_here, Wbar[r], Tbar[r], nubar[r])
-    # whitening adjoint: Wbar_ss += tril(Tbar_s Lu_s^T + nubar_s m_s^T); Lu_bar_s = sum_h W_ss^T Tbar_s ; m_bar_s = sum_h W_ss^T nubar_s
-    Wd, Wbd = _blocks(W[r], S, M), _blocks(Wbar[r], S, M)
-    nub5 = nubar[r].reshape(Hs, Cs, S, M, 1)
-    ops.gemm(Tbar[r], LuB[:, c0:c1].transpose(-1, -2), Wbd, beta=1., a_tri='lower', b_tri='upper', c_tri='lower',
-             tag='whiten_adj', zeroed=True)
-    ops.gemm(nub5, mB[:, c0:c1].unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
     s0 = S - Sg
-    ops.gemm(Wd[:, :, s0:].transpose(-1, -2), Tbar[r][:, :, s0:], Lubar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
-             a_tri='upper', b_tri='lower', c_tri='lower', tag='whiten_adj', zeroed=True)
-    ops.gemm(Wd[:, :, s0:].transpose(-1, -2), nub5[:, :, s0:], mbar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
-             a_tri='upper', tag='whiten_adj', zeroed=True)
+    if use_wb:
+      # N = blockdiag(T_s T_s^T) + eps W W^T  =>  Wbar += tril(2 eps G W) by GEMM; everything that lives on the M x M task
+      # blocks (Tbar_s = tril(2 G_ss T_s), the KL adjoint, the whitening adjoint into Wbar_ss, Lubar, mbar) in ONE
+      # shared-memory kernel (whiten.cu) instead of a GEMM, the KL kernel and four more products
+      if have_data:
+        ops.gemm(Gm[r], W[r], Wbar[r], alpha=2. * JITTER, beta=1., b_tri='lower', c_tri='lower', tag='Wbar+=2eps*G*W',
+                 zeroed=True)
+      ops.whiten_bwd(W, T, nu, Lu_all, m_all, Gm, nubar, g_kl, Wbar, Lubar_h, mbar_h, s_grad0=s0, rect=(h0, h1, c0, c1))
+    else:
+      if have_data:
+        # N = blockdiag(T_s T_s^T) + eps W W^T  =>  Tbar_s = tril(2 G_ss T_s),  Wbar += tril(2 eps G W)
+        ops.gemm(_blocks(Gm[r], S, M), T[r], Tbar[r], alpha=2., b_tri='lower', c_tri='lower', tag='Tbar=2*Gss*T',
+                 zeroed=True)
+        ops.gemm(Gm[r], W[r], Wbar[r], alpha=2. * JITTER, beta=1., b_tri='lower', c_tri='lower', tag='Wbar+=2eps*G*W',
+                 zeroed=True)
+      if g_kl is not None:
+        # adds (g_kl/H) T_t, (g_kl/H) nu_t and -(g_kl/H)/W_ii on the last block (the kernel divides by ITS H)
+        if Hs == H:
+          g_here = g_kl
+        else:
+          if g_kl_r is None:
+            g_kl_r = g_kl * (1.0 / H)
+          g_here = g_kl_r
+        ops.kl_bwd(W[r], T[r], nu[r], M, g_here, Wbar[r], Tbar[r], nubar[r])
+      # whitening adjoint: Wbar_ss += tril(Tbar_s Lu_s^T + nubar_s m_s^T); Lu_bar_s = sum_h W_ss^T Tbar_s ; m_bar_s = sum_h W_ss^T nubar_s
+      Wd, Wbd = _blocks(W[r], S, M), _blocks(Wbar[r], S, M)
+      nub5 = nubar[r].reshape(Hs, Cs, S, M, 1)
+      ops.gemm(Tbar[r], LuB[:, c0:c1].transpose(-1, -2), Wbd, beta=1., a_tri='lower', b_tri='upper', c_tri='lower',
+               tag='whiten_adj', zeroed=True)
+      ops.gemm(nub5, mB[:, c0:c1].unsqueeze(-2), Wbd, beta=1., c_tri='lower', tag='whiten_adj')
+      ops.gemm(Wd[:, :, s0:].transpose(-1, -2), Tbar[r][:, :, s0:], Lubar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
+               a_tri='upper', b_tri='lower', c_tri='lower', tag='whiten_adj', zeroed=True)
+      ops.gemm(Wd[:, :, s0:].transpose(-1, -2), nub5[:, :, s0:], mbar_h[h0:h1, :, c0:c1].permute(0, 2, 1, 3, 4),
+               a_tri='upper', tag='whiten_adj', zeroed=True)
     # Cholesky-inverse adjoint:  Kbar = -W^T Xi W,  Xi = (Phi(X) + Phi(X)^T)/2,  X = tril(Wbar W^T)
     ops.gemm(Wbar[r], W[r].transpose(-1, -2), X[r], a_tri='lower', b_tri='upper', c_tri='lower', tag='X=Wbar*Wt',
              zeroed=True)

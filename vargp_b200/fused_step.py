@@ -69,10 +69,11 @@ class FusedElbo:
         p.grad = torch.empty_like(p)
     # ---- draws, in the reference's order ----
     eps_theta = torch.empty(H, D + 1, device=dev, dtype=dt).normal_()
-    # ---- per-step arena: [terms(3) | kl pad | info(G) | nll workspace], one fill ----
-    nw = ops.nll_work(H, B)
-    arena = torch.zeros(4 + G + nw, device=dev, dtype=dt)
-    terms, info, work = arena[:3], arena[4:4 + G].view(torch.int32), arena[4 + G:]
+    # ---- per-step arena: [terms(3) | pad | info(G) | whiten workspace(1 + G) | nll workspace], one fill ----
+    nw, ww = ops.nll_work(H, B), ops.whiten_work(H, C)
+    arena = torch.zeros(4 + G + ww + nw, device=dev, dtype=dt)
+    terms, info = arena[:3], arena[4:4 + G].view(torch.int32)
+    wwork, work = arena[4 + G:4 + G + ww], arena[4 + G + ww:]
     theta = torch.empty(H, D + 1, device=dev, dtype=dt)
     ops.hyper_fwd(kern.log_mean.detach(), kern.log_logvar.detach(), kern.prior_log_mean, kern.prior_log_logvar, eps_theta,
                   theta, terms[0])
@@ -80,7 +81,7 @@ class FusedElbo:
                       self.Lu_all[S - 1])
     ctx = elbo._Ctx()
     f_mean, f_var, _, _, _ = elbo.marginal_forward(theta, self.Zcat, x, self.m_all, self.Lu_all, M, True, ctx,
-                                                   shard=self.shard, zeroed=(info, terms[1]))
+                                                   shard=self.shard, zeroed=(info, terms[1], wwork))
     gp._last_info = info
     if gp.n_prev:
       # the reference draws u_<t here (vargp.py:138); with ep_var_mean=True nothing depends on it -- the draw is issued

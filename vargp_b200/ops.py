@@ -79,6 +79,12 @@ def _load():
   lib.vargp_rbf_bwd_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_rbf_bwd_xside.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp, vp, vp]
   lib.vargp_softmax_nll.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, ctypes.c_float, vp, vp]
+  lib.vargp_whiten_fwd_work.argtypes = [i64, i64]
+  lib.vargp_whiten_fwd_work.restype = i64
+  lib.vargp_whiten_max_m.argtypes = [ctypes.c_int]
+  lib.vargp_whiten_max_m.restype = i64
+  lib.vargp_whiten_fwd.argtypes = [vp, vp, vp] + [i64] * 9 + [vp] * 6
+  lib.vargp_whiten_bwd.argtypes = [vp] * 8 + [i64] * 10 + [vp] * 4
   lib.vargp_step_assemble.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
   lib.vargp_step_grad_finish.argtypes = [vp, vp, i64, vp, i64] + [vp] * 10 + [i64] * 5 + [vp] * 6
   lib.vargp_softmax_nll_work.argtypes = [i64, i64]
@@ -133,7 +139,7 @@ class CudaOps:
 
   # -- per-launch device timing (bench.py roofline pass) ------------------------------------------
   _STREAM_OPS = ('scale_rows', 'rbf_bwd_prep', 'rbf_bwd_finish', 'rbf_bwd_xside', 'chol', 'trtri', 'chol_inv', 'tril_unpack',
-                 'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'marginal_reduce', 'marginal_bwd_prep',
+                 'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'whiten_fwd', 'whiten_bwd', 'step_assemble', 'step_grad_finish', 'marginal_reduce', 'marginal_bwd_prep',
                  'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step', 'hyper_fwd', 'hyper_bwd')
 
   def profile_start(self):
@@ -407,6 +413,35 @@ class CudaOps:
     C, M = Lu_t.shape[0], Lu_t.shape[-1]
     self._check(self.lib.vargp_kl_bwd_lu(_f32(Lu_t, 'Lu_t'), _f32(g_kl, 'g_kl'), C, M, _f32(Lu_bar_t, 'Lu_bar_t'),
                                          self._stream(Lu_t)), 'kl_bwd_lu')
+
+  # -- whitening on the diagonal task blocks (shared-memory kernels, small M) --------------------
+  def whiten_max_m(self, adjoint):
+    return int(self.lib.vargp_whiten_max_m(int(bool(adjoint))))
+
+  def whiten_work(self, H, C):
+    return int(self.lib.vargp_whiten_fwd_work(H, C))
+
+  def whiten_fwd(self, W, Lu_all, m_all, T, nu, N, kl, rect=None, work=None):
+    """T_s = W_ss Lu_s, nu_s = W_ss m_s, N_ss += T_s T_s^T, kl += (1/H) sum KL_hc on the (h, c) rectangle `rect`."""
+    H, C, P, _ = W.shape
+    S, M = Lu_all.shape[0], Lu_all.shape[-1]
+    h0, h1, c0, c1 = rect or (0, H, 0, C)
+    if kl is not None and work is None:
+      work = torch.zeros(self.whiten_work(H, C), device=W.device, dtype=W.dtype)
+    self._check(self.lib.vargp_whiten_fwd(_f32(W, 'W'), _f32(Lu_all, 'Lu_all'), _f32(m_all, 'm_all'), H, C, S, M, P, h0, h1, c0, c1,
+                                          _f32(T, 'T'), _f32(nu, 'nu'), _f32(N, 'N'), None if kl is None else _f32(kl, 'kl'),
+                                          None if kl is None else _f32(work, 'work'), self._stream(W)), 'whiten_fwd')
+
+  def whiten_bwd(self, W, T, nu, Lu_all, m_all, G, nubar, g_kl, Wbar, Lubar, mbar, s_grad0=0, rect=None):
+    H, C, P, _ = W.shape
+    S, M = Lu_all.shape[0], Lu_all.shape[-1]
+    h0, h1, c0, c1 = rect or (0, H, 0, C)
+    if tuple(Lubar.shape) != (H, S - s_grad0, C, M, M) or mbar.numel() != H * (S - s_grad0) * C * M:
+      raise VargpError('whiten_bwd: Lubar / mbar must be (H, S - s_grad0, C, M, M) / (H, S - s_grad0, C, M[, 1])')
+    self._check(self.lib.vargp_whiten_bwd(_f32(W, 'W'), _f32(T, 'T'), _f32(nu, 'nu'), _f32(Lu_all, 'Lu_all'), _f32(m_all, 'm_all'),
+                                          _f32(G, 'G'), _f32(nubar, 'nubar'), None if g_kl is None else _f32(g_kl, 'g_kl'),
+                                          H, C, S, M, P, h0, h1, c0, c1, s_grad0, _f32(Wbar, 'Wbar'), _f32(Lubar, 'Lubar'),
+                                          _f32(mbar, 'mbar'), self._stream(W)), 'whiten_bwd')
 
   # -- predictive marginal --------------------------------------------------------------------
   def marginal_reduce(self, V, NV, nu, theta, f_mean, f_var):
