@@ -47,7 +47,8 @@ struct TcCfg {
 // ---------------------------------------------------------------------------------------------
 template <int TC_BN, int TC_STAGES, int MINB>
 __global__ void __launch_bounds__(TC_THREADS, MINB)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   using Cfg = TcCfg<TC_BN, TC_STAGES>;
   constexpr int B_TILE = Cfg::B_TILE;
   constexpr int TC_TMEM_COLS = Cfg::TMEM_COLS;
@@ -93,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -291,7 +293,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //      and 32 sectors per request).  Row-major C: every 32 x 32 block is transposed through a padded per-warp
     //      tile carved out of the (now idle: all MMAs have retired) operand ring, so that a lane owns a COLUMN and a
     //      warp writes one 128 B line per instruction, eight rows in flight.  Other layouts keep lanes along m. ----
-    {
+    if (p.tma_store) {
+      // ---- TMA store.  A thread owns ROW m; it applies the epilogue to its 32-column chunks and lays them down in a
+      //      per-warp staging box (32 rows x 128 B, SWIZZLE_128B: 16 B group g of row r sits at (g ^ (r & 7)), which also
+      //      makes the 32 float4 stores of a warp bank-conflict free), carved out of the idle operand ring.  One elected
+      //      lane hands the box to the TMA engine (cp.async.bulk.tensor store, or cp.reduce ... add for beta == 1); rows /
+      //      columns beyond M / N are clipped by the tensor map.  No transposition pass, no per-thread global stores:
+      //      the tail of a tile shrinks from ~4.5 us to the time it takes to fill the staging boxes. ----
+      const int Mi = (int)p.M, Ni = (int)p.N;
+      const int mrow = (int)m0 + quad * 32;
+      const bool rbf = p.epi != VARGP_EPI_NONE, sym = p.epi == VARGP_EPI_RBF_SYM;
+      const bool add = p.tma_store == 2;
+      uint8_t* box0 = smem + (size_t)(warp - 6) * (EC / 32) * 4096;
+      bool any = false;
+      if (!(add && nk == 0)) {             // culled tile of an accumulating product: nothing to add
+#pragma unroll
+        for (int c = 0; c < EC / 32; ++c) {
+          const int nc0 = (int)n0 + half * EC + c * 32;
+          if (nc0 >= Ni || mrow >= Mi) break;                                  // warp-uniform
+          float cn = 0.f;
+          if (rbf && nc0 + lane < Ni) cn = 0.5f * e_col[nc0 + lane];
+          const uint32_t rowb = smem_u32(box0 + c * 4096) + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = g4 * 4 + u;
+              const int64_t n = nc0 + j;
+              float x = acc[c * 32 + j];
+              if (rbf) {
+                const float coln = __shfl_sync(0xffffffffu, cn, j);
+                x = gamma2 * expf(x - rown - coln);
+                if (sym && m == n) x = gamma2;
+              }
+              x *= p.alpha;
+              if ((p.tri_c == VARGP_TRI_LOWER && n > m) || (p.tri_c == VARGP_TRI_UPPER && n < m)) x = 0.f;
+              v[u] = x;
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (uint32_t)((g4 ^ (lane & 7)) << 4)),
+                         "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          }
+          any = true;
+        }
+      }
+      if (any) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < EC / 32; ++c) {
+            const int nc0 = (int)n0 + half * EC + c * 32;
+            if (nc0 >= Ni) break;
+            tma_store_5d(&tmC, box0 + c * 4096, nc0, mrow, i2, i1, i0, add);
+          }
+          tma_store_commit_wait();
+        }
+      }
+    } else {
       float* tile_f = reinterpret_cast<float*>(smem) + (warp - 6) * (32 * 33);
       const uint32_t tile = smem_u32(tile_f);
       const int Mi = (int)p.M, Ni = (int)p.N;
@@ -384,6 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 long long* g_tc_dbg = nullptr;
+bool g_tma_store = true;         // VARGP_TMA_STORE=0: keep the shared-memory transposition + st.global epilogue
 EncodeTiledFn g_encode = nullptr;
 bool g_tc_ready = false;
 
@@ -404,6 +464,8 @@ int vargp_tc_init() {
   g_encode = (EncodeTiledFn)fn;
   e = cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128, 3>::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
+  const char* ts = getenv("VARGP_TMA_STORE");
+  if (ts) g_tma_store = atoi(ts) != 0;
   int rc = tc2_init();
   if (rc) return rc;
   g_tc_ready = true;
@@ -447,10 +509,23 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   if (rc) return rc;
 
   // large problems: persistent 2-CTA kernel with 256 x 256 tiles (gemm_tc2.cu)
+  p.tma_store = 0;
   if (big) return tc2_launch(tmA, tmB, p, (cudaStream_t)stream);
 
+  // C through the TMA engine when it is row-major with 16 B-aligned rows / batches and beta is 0 or 1
+  alignas(64) CUtensorMap tmC = tmA;
+  if (g_tma_store && g->c_cs == 1 && (g->beta == 0.f || g->beta == 1.f)) {
+    int32_t use_c[3];
+    if (make_map(&tmC, g->C, g->M, g->N, g->c_rs, 1, g->nb, g->c_bs, false, use_c, 32) == 0) {
+      bool ok = true;
+      for (int i = 0; i < 3; ++i) ok = ok && (use_c[i] || g->nb[i] == 1);       // a broadcast C cannot be stored to
+      if (ok) p.tma_store = g->beta == 0.f ? 1 : 2;
+    }
+    if (!p.tma_store) tmC = tmA;
+  }
+
   dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
-  launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, p);
+  launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, tmC, p);
   return launch_status();
 }
 

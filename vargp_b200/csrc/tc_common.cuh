@@ -28,6 +28,7 @@ struct TcParams {
   int32_t a_mn, b_mn;            // 1: operand is M/N-contiguous (MN-major), 0: K-contiguous
   int32_t a_b[3], b_b[3];        // 1 if the operand really varies along that batch dim (else coordinate 0)
   long long* dbg;                // optional: 8 clock64() stamps of CTA 0's pipeline (vargp_tc_debug; profiling only)
+  int32_t tma_store;             // 1-CTA kernel: C goes out through cp.async.bulk.tensor stores (tmC valid); 2 = reduce-add (beta == 1)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -63,6 +64,22 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3), "r"(c4) : "memory");
+}
+
+// smem (32 x 32 fp32 box, SWIZZLE_128B) -> global through the tensor map; `add`: C += box (cp.reduce, fp32 add at L2)
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3, int c4,
+                                             bool add) {
+  if (!add) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  } else {
+    asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging tile may be released (CTA exit)
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {

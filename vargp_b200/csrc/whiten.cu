@@ -44,10 +44,24 @@ __device__ __forceinline__ void block_mm(const float* __restrict__ A, const floa
 }
 
 // M x M block at src (row stride lds) -> shared memory (row stride ld), rows / columns >= M zero-filled up to Mp
-__device__ __forceinline__ void load_block(float* dst, int ld, const float* __restrict__ src, int64_t lds, int M, int Mp) {
-  for (int e = threadIdx.x; e < Mp * Mp; e += blockDim.x) {
-    const int i = e / Mp, j = e - i * Mp;
-    dst[i * ld + j] = (i < M && j < M) ? src[(int64_t)i * lds + j] : 0.f;
+// (Mp = 16 R is a multiple of 16, so Mp * Mp is a multiple of the 256 threads: 8 independent loads per thread in flight)
+__device__ __forceinline__ void load_block(float* __restrict__ dst, int ld, const float* __restrict__ src, int64_t lds, int M,
+                                           int Mp) {
+  constexpr int U = 8;
+  for (int e0 = threadIdx.x; e0 < Mp * Mp; e0 += U * WT * WT) {
+    float v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int e = e0 + q * WT * WT;
+      const int i = e / Mp, j = e - i * Mp;
+      v[q] = (e < Mp * Mp && i < M && j < M) ? __ldg(src + (int64_t)i * lds + j) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int e = e0 + q * WT * WT;
+      const int i = e / Mp, j = e - i * Mp;
+      if (e < Mp * Mp) dst[i * ld + j] = v[q];
+    }
   }
 }
 
