@@ -374,7 +374,7 @@ def run_workload(ctx, wl, task, K, Wm, want_e2e=True, batch=None):
   #      collectives); only rank 0's record is reported. ----
   stepper.use_graph = False
   side, elbo.USE_SIDE_STREAM = elbo.USE_SIDE_STREAM, False
-  pdl = ops.set_pdl(False)
+  pdl = ops.set_pdl(0)
   step(0)                                              # warm the eager allocator pool of this schedule
   ops.profile_start()
   nprof = 3

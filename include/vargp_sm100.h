@@ -57,15 +57,19 @@ typedef struct {
   int64_t e_row_bs[3], e_col_bs[3];
   const float* e_theta; /* gamma2 = exp(2 * e_theta[batch offset via e_theta_bs + e_D]) */
   int64_t e_theta_bs[3], e_D;
+  /* scheduling hint: a product that runs BESIDE a critical chain (side stream) may be told to occupy at most this many
+   * SMs (0 = all).  Honoured by the persistent 2-CTA kernel, whose CTAs would otherwise own every SM until it is done. */
+  int64_t sm_limit;
 } vargp_gemm_t;
 
 int vargp_init(int device);
 const char* vargp_version(void);
 const char* vargp_strerror(int code);
-/* programmatic dependent launch between the library's kernels (on by default; VARGP_PDL=0 in the environment of
- * vargp_init also disables it).  bench.py switches it off for its serialised per-kernel timing pass.  Returns the
- * previous setting. */
-int vargp_set_pdl(int on);
+/* programmatic dependent launch between the library's kernels: 0 off, 1 on every launch, 2 (default) only on launches
+ * with a small shared-memory footprint (a parked tensor-core GEMM CTA would take its SM away from the grid it waits
+ * for).  Also settable through VARGP_PDL in the environment of vargp_init.  bench.py switches it off for its serialised
+ * per-kernel timing pass.  Returns the previous setting. */
+int vargp_set_pdl(int mode);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t vargp_launch_count(void);
 
@@ -121,6 +125,13 @@ int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t
 int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                          float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                          int32_t* info, int64_t info_base, int accumulate, void* stream);
+/* Whole-matrix shared-memory variant for n <= 320 (one CTA per matrix, packed 32 x 32 blocks, factorisation and in-place
+ * inverse without leaving the SM; potrf_mid.cu): what vargp_chol_inv takes for 128 < n <= 320.  A, L, W must not alias.
+ * vargp_chol_mid_config: largest n routed to it (0 disables, < 0 only queries); returns the previous setting. */
+int vargp_chol_inv_mid(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                       float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                       int32_t* info, void* stream);
+int64_t vargp_chol_mid_config(int64_t max_n);
 /* block size (multiple of 32; 0 keeps it) and minimum n (< 0 keeps it) of the blocked path;
  * returns (min_n << 32) | block after the update. */
 int64_t vargp_chol_config(int64_t block, int64_t min_n);

@@ -23,7 +23,7 @@ class EmuOps:
     dst.copy_(src.unsqueeze(0) * torch.exp(-theta[:, :D]).unsqueeze(1))
     norms.copy_((dst * dst).sum(-1))
 
-  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag=None):
+  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag=None, sm_limit=0):
     g2 = torch.exp(2. * theta[:, -1]).view(-1, 1, 1, 1)
     dot = a @ b.transpose(-1, -2)
     val = g2 * torch.exp(dot - 0.5 * an.unsqueeze(-1) - 0.5 * bn.unsqueeze(-2))
@@ -32,7 +32,7 @@ class EmuOps:
       val = torch.where(eye, g2.expand_as(val), val)
     out.copy_(val)
 
-  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag=None, zeroed=False):
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag=None, zeroed=False, sm_limit=0):
     prod = alpha * (_tri(A, a_tri) @ _tri(B, b_tri))
     if c_tri is not None:
       prod = _tri(prod, c_tri)

@@ -35,8 +35,8 @@ def test_library_exports_every_declared_symbol():
 def test_gemm_descriptor_layout_matches_header():
   """ctypes mirror and the C struct must agree on size (field order is checked by the GPU tests)."""
   from vargp_b200.ops import GemmDesc
-  # 3 ptr + 3 + 6 + 3 + 9 int64, 2 float, 4 int32, 2 ptr, 6 int64, 1 ptr, 4 int64
-  expect = 8 * (3 + 3 + 6 + 3 + 9) + 4 * 2 + 4 * 4 + 8 * 2 + 8 * 6 + 8 + 8 * 4
+  # 3 ptr + 3 + 6 + 3 + 9 int64, 2 float, 4 int32, 2 ptr, 6 int64, 1 ptr, 4 int64, 1 int64 (sm_limit)
+  expect = 8 * (3 + 3 + 6 + 3 + 9) + 4 * 2 + 4 * 4 + 8 * 2 + 8 * 6 + 8 + 8 * 4 + 8
   assert ctypes.sizeof(GemmDesc) == expect
 
 

@@ -5,7 +5,7 @@
 
 namespace vargp {
 int64_t g_launches = 0;
-bool g_pdl = true;
+int g_pdl = 2;
 int g_device = -1;
 }  // namespace vargp
 
@@ -25,9 +25,9 @@ extern "C" const char* vargp_strerror(int code) {
 
 extern "C" int64_t vargp_launch_count(void) { return g_launches; }
 
-extern "C" int vargp_set_pdl(int on) {
-  const int old = g_pdl ? 1 : 0;
-  g_pdl = on != 0;
+extern "C" int vargp_set_pdl(int mode) {
+  const int old = g_pdl;
+  g_pdl = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return old;
 }
 
@@ -44,6 +44,6 @@ extern "C" int vargp_init(int device) {
   if (prop.major != 10) return VARGP_ERR_UNSUPPORTED;   // sm_100a only: no other code path exists
   g_device = device;
   const char* pdl = getenv("VARGP_PDL");
-  if (pdl) g_pdl = atoi(pdl) != 0;
+  if (pdl) vargp_set_pdl(atoi(pdl));
   return vargp_tc_init();
 }

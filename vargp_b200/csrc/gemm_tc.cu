@@ -495,6 +495,7 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   p.tri_a = g->tri_a; p.tri_b = g->tri_b; p.tri_c = g->tri_c; p.epi = g->epi;
   p.e_row = g->e_row; p.e_col = g->e_col; p.e_theta = g->e_theta; p.e_D = g->e_D;
   p.dbg = g_tc_dbg;
+  p.sm_limit = (int32_t)(g->sm_limit > 0 && g->sm_limit < (1 << 20) ? g->sm_limit : 0);
   // prefer the K-major form when a dimension of size 1 makes both strides look contiguous
   p.a_mn = (a_k && !(a_mn && g->K == 1)) ? 0 : 1;
   p.b_mn = (b_k && !(b_mn && g->K == 1)) ? 0 : 1;

@@ -579,7 +579,8 @@ bool tc2_wants(const vargp_gemm_t* g) {
 
 int tc2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
   const int64_t tiles = ceil_div(p.M, T2_BM) * ceil_div(p.N, T2_BN) * p.nb[0] * p.nb[1] * p.nb[2];
-  const int64_t ncl = tiles < g_t2_clusters ? tiles : g_t2_clusters;
+  int64_t ncl = tiles < g_t2_clusters ? tiles : g_t2_clusters;
+  if (p.sm_limit >= 2 && ncl > p.sm_limit / 2) ncl = p.sm_limit / 2;        // leave SMs to the chain this product runs beside
   int c_vec4 = (p.c_cs == 1 && p.c_rs % 4 == 0 && reinterpret_cast<uintptr_t>(p.C) % 16 == 0) ? 1 : 0;
   for (int i = 0; i < 3; ++i)
     if (p.nb[i] > 1 && p.c_bs[i] % 4 != 0) c_vec4 = 0;

@@ -28,6 +28,7 @@ struct TcParams {
   int32_t a_mn, b_mn;            // 1: operand is M/N-contiguous (MN-major), 0: K-contiguous
   int32_t a_b[3], b_b[3];        // 1 if the operand really varies along that batch dim (else coordinate 0)
   long long* dbg;                // optional: 8 clock64() stamps of CTA 0's pipeline (vargp_tc_debug; profiling only)
+  int32_t sm_limit;              // 2-CTA kernel: at most this many CTAs (0 = one per SM)
   int32_t tma_store;             // 1-CTA kernel: C goes out through cp.async.bulk.tensor stores (tmC valid); 2 = reduce-add (beta == 1)
 };
 

@@ -53,6 +53,8 @@ STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '1') != '0'
 V_SIDE = os.environ.get('VARGP_V_SIDE', '1') != '0'
 # VARGP_WHITEN=0: the per-task-block products through the batched GEMMs even when M fits the shared-memory kernels
 USE_WHITEN = os.environ.get('VARGP_WHITEN', '1') != '0'
+# SMs the persistent Kzx GEMM may occupy while it runs beside Kzz -> Cholesky (148 - H*C - a margin at the benched shape)
+SIDE_SM_LIMIT = int(os.environ.get('VARGP_SIDE_SM_LIMIT', '112'))
 
 
 class _Fork:
@@ -236,8 +238,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
       with fork:
         ops.scale_rows(x, theta, xs, xn)
         if STACK_CLASSES:
+          # (beside the factorisation chain, whose shared-memory kernels need H*C SMs: the persistent GEMM leaves them free)
           ops.rbf_gram(zs.view(H, 1, C * P, D), zn.view(H, 1, C * P), xs.view(H, 1, B, D), xn.view(H, 1, B), theta,
-                       Kzx.view(H, 1, C * P, B), False, tag='Kzx')
+                       Kzx.view(H, 1, C * P, B), False, tag='Kzx', sm_limit=SIDE_SM_LIMIT)
         else:
           ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
 

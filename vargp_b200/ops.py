@@ -37,6 +37,7 @@ class GemmDesc(ctypes.Structure):
     ('e_row_bs', i64 * 3), ('e_col_bs', i64 * 3),
     ('e_theta', vp),
     ('e_theta_bs', i64 * 3), ('e_D', i64),
+    ('sm_limit', i64),
   ]
 
 
@@ -65,6 +66,8 @@ def _load():
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
   lib.vargp_chol_inv.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
+  lib.vargp_chol_mid_config.argtypes = [i64]
+  lib.vargp_chol_mid_config.restype = i64
   lib.vargp_chol_config.argtypes = [i64, i64]
   lib.vargp_chol_config.restype = i64
   lib.vargp_tril_unpack.argtypes = [vp, i64, i64, vp, vp]
@@ -199,9 +202,10 @@ class CudaOps:
   def launch_count(self):
     return int(self.lib.vargp_launch_count())
 
-  def set_pdl(self, on):
-    """Programmatic dependent launch between the library's kernels on / off; returns the previous setting."""
-    return bool(self.lib.vargp_set_pdl(int(bool(on))))
+  def set_pdl(self, mode):
+    """Programmatic dependent launch between the library's kernels: 0 off, 1 every launch, 2 light kernels only
+    (default); returns the previous setting."""
+    return int(self.lib.vargp_set_pdl(int(mode)))
 
   def tc2_config(self, min_tiles=None):
     """Set (or with None query) the tile-count threshold above which GEMMs take the 2-CTA kernel; < 0 disables."""
@@ -264,13 +268,15 @@ class CudaOps:
     self._check(self._timed(tag, 'gemm_simt', flops, nbytes, lambda: self.lib.vargp_gemm(ctypes.byref(d), s)),
                 'vargp_gemm')
 
-  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag='gemm', zeroed=False):
+  def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag='gemm', zeroed=False, sm_limit=0):
     """C = alpha tri_a(A) tri_b(B) [tri_c] + beta C.  `zeroed=True` promises that the other triangle of a
-    declared-triangular operand holds actual zeros (lets the TMA-fed tensor-core kernel take the call)."""
+    declared-triangular operand holds actual zeros (lets the TMA-fed tensor-core kernel take the call).
+    `sm_limit`: at most that many SMs for a product that runs beside a critical chain (persistent 2-CTA kernel)."""
     d, _ = self._desc(A, B, C, alpha, beta, a_tri, b_tri, c_tri)
+    d.sm_limit = int(sm_limit)
     self._run_gemm(d, C, tag, zeroed)
 
-  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram'):
+  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram', sm_limit=0):
     """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}."""
     _f32(theta, 'theta', contiguous=False)
     d, nb = self._desc(a, b.transpose(-1, -2), out, 1., 0., None, None, None)
@@ -289,6 +295,7 @@ class CudaOps:
     th = theta.as_strided((H,) + (1,) * (out.dim() - 3) + (1, 1), (theta.stride(0),) + (0,) * (out.dim() - 3) + (1, 1))
     d.e_theta_bs = (i64 * 3)(*_bstrides(th, nb))
     d.e_D = theta.shape[1] - 1
+    d.sm_limit = int(sm_limit)
     self._run_gemm(d, out, tag)
 
   # -- RBF operand prep / adjoint -------------------------------------------------------------
@@ -378,6 +385,10 @@ class CudaOps:
       raise VargpError('chol_inv: shape mismatch')
     self._check(self.lib.vargp_chol_inv(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
                                         info.data_ptr(), self._stream(L)), 'chol_inv')
+
+  def chol_mid_config(self, max_n=-1):
+    """Largest n that vargp_chol_inv routes to the whole-matrix shared-memory kernel (0 disables); returns the previous value."""
+    return int(self.lib.vargp_chol_mid_config(int(max_n)))
 
   def chol_config(self, block=0, min_n=-1):
     """Set block size / minimum n of the blocked factorisation; returns (block, min_n) in effect."""
