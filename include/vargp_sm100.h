@@ -256,6 +256,18 @@ int vargp_step_grad_finish(const float* Zbar, const float* mbar, int64_t mbar_hs
 int vargp_yogi_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
                     float eps, float* pows, void* stream);
 
+/* Data-parallel tail of the step as one compute + collective pair over NVLink peer memory (peer.cu): gradient
+ * all-reduce (one-shot: every rank reads all ranks' staged gradients in rank order, so the sum is bit-identical
+ * everywhere) fused with the Yogi update of vargp_yogi_step.  peer_bufs: HOST array of `world` DEVICE pointers, entry r =
+ * rank r's buffer of vargp_peer_buffer_floats(n) floats in symmetric (peer-mapped) memory, zero-filled once before the
+ * first step (the host side allocates and exchanges them, e.g. torch.distributed._symmetric_memory); ctr: 4 zero-initialised
+ * device words owned by this rank.  n must be a multiple of 4 and flat_g / p / m / v 16-byte aligned.  On return (stream
+ * order) flat_g holds the summed gradient and p, m, v, pows are advanced.  One cross-GPU synchronisation per call; every
+ * rank must make the same sequence of calls. */
+int64_t vargp_peer_buffer_floats(int64_t n);
+int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int rank, int64_t n, float* flat_g, float* p, float* m,
+                              float* v, float lr, float b1, float b2, float eps, float* pows, uint32_t* ctr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,8 +23,15 @@ from vargp_b200.train import ElboStepper                    # noqa: E402
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
 dev = torch.device('cuda', local)
-dist.init_process_group('nccl', device_id=dev)
+import datetime                                           # noqa: E402
+dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
 out = {}
+PARTS = os.environ.get('VARGP_DIST_PARTS', 'grad,graph').split(',')
+
+
+def mark(msg):
+  print(f'[dist_worker rank {rank}] {msg}', file=sys.stderr, flush=True)
+
 
 
 def relerr(a, b):
@@ -34,6 +41,9 @@ def relerr(a, b):
 # ---- 1. gradients: N ranks vs one rank on the full batch ----
 for name, kw in (('replicated', dict(C=10, D=784, M=60, t=2, B=128 * world, sigma=10., seed=5)),
                  ('sharded', dict(C=10, D=784, M=640, t=0, B=256 * world, sigma=10., seed=6))):
+  if 'grad' not in PARTS:
+    break
+  mark(f'part 1 {name}')
   params, prev, x, y, noise = make_case(**kw)
   B = x.size(0) // world
   beta, N = 1.7, 10. * x.size(0)
@@ -64,22 +74,31 @@ for name, kw in (('replicated', dict(C=10, D=784, M=60, t=2, B=128 * world, sigm
 # ---- 2. NCCL inside the step graph vs the eager data-parallel step ----
 for name, kw in (('graph', dict(C=10, D=784, M=60, t=2, B=128, sigma=10., seed=7)),
                  ('graph_sharded', dict(C=10, D=784, M=640, t=0, B=256, sigma=10., seed=8))):
+  if 'graph' not in PARTS:
+    break
   res = {}
   for mode in ('eager', 'graph'):
+    mark(f'part 2 {name} {mode}')
     params, prev, x, y, _ = make_case(**kw)
     gp = util.build_model(params, prev, 3, 10, {}, dev, torch.float32)
     g = torch.Generator().manual_seed(100 + rank)
     xs = torch.rand(4, kw['B'], 784, generator=g).to(dev)
     ys = torch.randint(0, 10, (4, kw['B']), generator=g).to(dev)
+    # eager: NCCL all_reduce + yogi_step launched from the host; graph: one graph launch per step with the fused
+    # peer-memory all-reduce + Yogi kernels (and, factor-sharded, the NCCL all-gathers / reduce-scatters) inside it
     st = ElboStepper(gp, n_data=10 * kw['B'] * world, batch_size=kw['B'], beta=1.7, lr=1e-2, world_size=world,
-                     use_graph=mode == 'graph')
+                     use_graph=mode == 'graph', peer=None if mode == 'graph' else False)
     torch.manual_seed(11)                       # identical theta draws on every rank
     for i in range(6):
       st.step(xs[i % 4], ys[i % 4])
+      if i == 0:
+        torch.cuda.synchronize()
+        mark(f'part 2 {name} {mode}: first step done')
     st.check_errors()
     torch.cuda.synchronize()
     res[mode] = (st.opt.flat_p.clone(), st.terms_vec.clone(), bool(getattr(st, '_tail_in_graph', False)),
                  st.shard is not None)
+    out[f'{name}_{mode}_peer_allreduce'] = bool(st.peer)
   out[f'{name}_param_relerr'] = relerr(res['graph'][0], res['eager'][0])
   out[f'{name}_terms_relerr'] = relerr(res['graph'][1], res['eager'][1])
   out[f'{name}_collectives_in_graph'] = res['graph'][2]
@@ -89,12 +108,16 @@ for name, kw in (('graph', dict(C=10, D=784, M=60, t=2, B=128, sigma=10., seed=7
   dist.broadcast(p0, 0)
   out[f'{name}_replica_drift'] = relerr(res['graph'][0], p0)
 
-ok = (out['replicated_grad_relerr'] < 2e-5 and out['sharded_grad_relerr'] < 2e-5 and
-      out['replicated_terms_relerr'] < 1e-5 and out['sharded_terms_relerr'] < 1e-5 and
-      out['graph_param_relerr'] < 1e-5 and out['graph_sharded_param_relerr'] < 1e-5 and
-      out['graph_collectives_in_graph'] and out['graph_sharded_collectives_in_graph'] and
-      out['graph_sharded_factor_sharded'] and not out['graph_factor_sharded'] and
-      out['graph_replica_drift'] == 0.0 and out['graph_sharded_replica_drift'] < 1e-6)
+mark('checks')
+ok = True
+if 'grad' in PARTS:
+  ok = ok and (out['replicated_grad_relerr'] < 2e-5 and out['sharded_grad_relerr'] < 2e-5 and
+               out['replicated_terms_relerr'] < 1e-5 and out['sharded_terms_relerr'] < 1e-5)
+if 'graph' in PARTS:
+  ok = ok and (out['graph_param_relerr'] < 1e-5 and out['graph_sharded_param_relerr'] < 1e-5 and
+               out['graph_collectives_in_graph'] and out['graph_sharded_collectives_in_graph'] and
+               out['graph_sharded_factor_sharded'] and not out['graph_factor_sharded'] and
+               out['graph_replica_drift'] == 0.0 and out['graph_sharded_replica_drift'] < 1e-6)
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 if rank == 0:

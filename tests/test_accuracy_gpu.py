@@ -133,11 +133,11 @@ def test_end_of_run_accuracy_matches_reference_path(name, cuda_ops):
     tasks, C, D = _toy_tasks(g)
     kw = dict(M=20, steps=300, B=100, lr=3e-2, beta=1.0, log_sigma=math.log(0.5))
   elif name == 'permuted_mnist_shape':   # experiments/vargp.py permuted_mnist: beta=1.64, all classes in every task
-    tasks, C, D = _permuted_tasks(g)
-    kw = dict(M=24, steps=80, B=128, lr=1e-2, beta=1.64, log_sigma=math.log(10.))
+    tasks, C, D = _permuted_tasks(g, n_tasks=3)
+    kw = dict(M=32, steps=120, B=128, lr=1e-2, beta=1.64, log_sigma=math.log(10.))
   else:                              # Split-MNIST shape (D=784, 10 output GPs, 2 classes per task), learned-lengthscale regime
-    tasks, C, D = _mnist_like_tasks(g)
-    kw = dict(M=20, steps=80, B=128, lr=1e-2, beta=10.0, log_sigma=math.log(10.))
+    tasks, C, D = _mnist_like_tasks(g, n_tasks=4)
+    kw = dict(M=32, steps=150, B=128, lr=1e-2, beta=10.0, log_sigma=math.log(10.))
   acc_o, pr_o = _run('oracle', tasks, C, D, **kw)
   acc_g, pr_g = _run('b200', tasks, C, D, **kw)
   print(name, 'oracle acc', [f'{a:.4f}' for a in acc_o], 'b200 acc', [f'{a:.4f}' for a in acc_g],
@@ -146,3 +146,54 @@ def test_end_of_run_accuracy_matches_reference_path(name, cuda_ops):
   for t, (a, b) in enumerate(zip(acc_o, acc_g)):
     assert a > chance + 0.2, f'task {t}: the oracle run did not learn ({a:.3f})'
     assert abs(a - b) <= 0.005 + 1e-9, f'task {t}: accuracy {b:.4f} vs reference path {a:.4f} (> 0.5 pt)'
+
+
+def test_fused_stepper_reaches_the_same_accuracy_at_the_benched_size(cuda_ops):
+  """Full Split-MNIST shape (C=10, D=784, M=60 per task, 5 tasks, B=512): the graph-replayed tape-free training step
+  (train.ElboStepper -> fused_step.FusedElbo, what bench.py times) against loss() + autograd + the same Yogi rule on the
+  same kernels (the path the fixtures and the oracle runs above validate).  Same seeds -> same minibatches and noise
+  streams; final per-task test accuracies must agree within 0.5 pt and the final parameters closely."""
+  from vargp_b200.train import ElboStepper
+  from vargp_b200.optim import FlatYogi
+  g = torch.Generator().manual_seed(4)
+  tasks, C, D = _mnist_like_tasks(g, n_tasks=5, n_train=1024, n_test=400)
+  M, steps, B, lr, beta, H, F = 60, 60, 512, 1e-2, 10.0, 3, 10
+  out = {}
+  for arm in ('autograd', 'fused'):
+    gi = torch.Generator().manual_seed(21)
+    prev, prior, final = [], None, None
+    torch.manual_seed(99)
+    for t, ((xtr, ytr), _) in enumerate(tasks):
+      p0 = _init_params(gi, xtr, C, D, M, math.log(10.), prior)
+      gp = util.build_model(p0, prev, H, F, {}, 'cuda', torch.float32)
+      N = xtr.size(0)
+      xd, yd = xtr.cuda(), ytr.cuda()
+      st = ElboStepper(gp, n_data=N, batch_size=B, beta=beta, lr=lr, use_graph=arm == 'fused', fused=arm == 'fused')
+      assert (st.fused is not None) == (arm == 'fused')
+      for s in range(steps):
+        idx = torch.randperm(N, generator=gi)[:B].cuda()
+        st.step(xd[idx], yd[idx])
+      st.check_errors()
+      cur = dict(p0, z=gp.z.detach().cpu(), u_mean=gp.u_mean.detach().cpu(), u_tril_vec=gp.u_tril_vec.detach().cpu(),
+                 log_mean=gp.kernel.log_mean.detach().cpu(), log_logvar=gp.kernel.log_logvar.detach().cpu())
+      final = (cur, list(prev))
+      prev = prev + [dict(z=cur['z'], u_mean=cur['u_mean'], u_tril_vec=cur['u_tril_vec'])]
+      prior = (cur['log_mean'], cur['log_logvar'])
+    cur, prv = final
+    ge = torch.Generator().manual_seed(5)
+    accs = []
+    for _, (xte, yte) in tasks:
+      nz = dict(eps_theta=torch.randn(H, D + 1, generator=ge), eps_f=torch.randn(H, 40, C, xte.size(0), generator=ge))
+      with torch.no_grad():
+        gpe = util.build_model(cur, prv, H, 40, {}, 'cuda', torch.float32)
+        pr = gpe.predict(xte.cuda(), noise={k: v.cuda() for k, v in nz.items()}).cpu()
+      accs.append((pr.argmax(-1) == yte).float().mean().item())
+    out[arm] = (accs, cur)
+  print('autograd acc', [f'{a:.4f}' for a in out['autograd'][0]], 'fused acc', [f'{a:.4f}' for a in out['fused'][0]])
+  for t, (a, b) in enumerate(zip(*[out[k][0] for k in ('autograd', 'fused')])):
+    assert a > 0.3, f'task {t}: the run did not learn ({a:.3f})'
+    assert abs(a - b) <= 0.005 + 1e-9, (t, a, b)
+  errs = {k: util.relerr(out['fused'][1][k], out['autograd'][1][k]) for k in ('z', 'u_mean', 'u_tril_vec', 'log_mean')}
+  print('final-parameter differences', {k: f'{v:.2e}' for k, v in errs.items()})
+  for k, v in errs.items():            # 300 Yogi steps apart only by summation order of a few float atomics
+    assert v < 5e-2, (k, v)

@@ -27,7 +27,7 @@ def test_nccl_data_parallel_step_matches_single_gpu():
   n = 2
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}', '--master-addr', '127.0.0.1',
          '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dist_worker_gpu.py')]
-  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
   assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
   rec = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
   assert rec['ok'] and rec['world'] == n, rec

@@ -94,6 +94,9 @@ def _load():
   lib.vargp_softmax_nll_work.restype = i64
   lib.vargp_softmax_predict.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp]
   lib.vargp_yogi_step.argtypes = [vp, vp, vp, vp, i64] + [ctypes.c_float] * 4 + [vp, vp]
+  lib.vargp_peer_buffer_floats.argtypes = [i64]
+  lib.vargp_peer_buffer_floats.restype = i64
+  lib.vargp_peer_allreduce_yogi.argtypes = [vp, ctypes.c_int, ctypes.c_int, i64, vp, vp, vp, vp] + [ctypes.c_float] * 4 + [vp, vp, vp]
   lib.vargp_hyper_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
   lib.vargp_hyper_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
   return lib
@@ -145,6 +148,9 @@ class CudaOps:
                  'tril_unpack_bwd', 'kl_fwd', 'kl_bwd', 'kl_bwd_lu', 'whiten_fwd', 'whiten_bwd', 'step_assemble', 'step_grad_finish', 'marginal_reduce', 'marginal_bwd_prep',
                  'sym_phi', 'nll_fwd_bwd', 'predict', 'yogi_step', 'hyper_fwd', 'hyper_bwd')
 
+  # positional tensor arguments that a kernel both reads and writes (Kbar of rbf_bwd_prep, X of sym_phi, p / m / v of Yogi)
+  _RMW_ARGS = {'rbf_bwd_prep': (0,), 'sym_phi': (0,), 'yogi_step': (0, 2, 3)}
+
   def profile_start(self):
     """Bracket every launch with CUDA events (slows the host side; never on during a timed region)."""
     self.prof = []
@@ -152,8 +158,9 @@ class CudaOps:
       fn = getattr(type(self), name)
 
       def timed(*a, _fn=fn, _name=name, **kw):
-        # algorithmic bytes of a streaming kernel: every tensor argument is touched once
+        # algorithmic bytes of a streaming kernel: every tensor argument is touched once, read-modify-write ones twice
         nbytes = sum(t.numel() * t.element_size() for t in a if isinstance(t, torch.Tensor))
+        nbytes += sum(a[i].numel() * a[i].element_size() for i in self._RMW_ARGS.get(_name, ()) if i < len(a))
         flops = 0.0
         if _name in ('chol', 'trtri', 'chol_inv'):
           n = a[0].shape[-1]
@@ -550,6 +557,19 @@ class CudaOps:
     self._check(self.lib.vargp_yogi_step(_f32(p, 'p'), _f32(g, 'g'), _f32(m, 'm'), _f32(v, 'v'), p.numel(),
                                          float(lr), float(b1), float(b2), float(eps), _f32(pows, 'pows'),
                                          self._stream(p)), 'yogi_step')
+
+
+  def peer_buffer_floats(self, n):
+    return int(self.lib.vargp_peer_buffer_floats(n))
+
+  def peer_allreduce_yogi(self, peer_ptrs, rank, flat_g, p, m, v, lr, b1, b2, eps, pows, ctr):
+    """flat_g <- sum over ranks (through the ranks' symmetric-memory staging buffers `peer_ptrs`), then the Yogi update."""
+    arr = (vp * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+    if ctr.dtype != torch.int32 or ctr.numel() < 4:
+      raise VargpError('peer_allreduce_yogi: ctr must be an int32 tensor of 4 words')
+    self._check(self.lib.vargp_peer_allreduce_yogi(arr, len(peer_ptrs), int(rank), p.numel(), _f32(flat_g, 'flat_g'), _f32(p, 'p'),
+                                                   _f32(m, 'm'), _f32(v, 'v'), float(lr), float(b1), float(b2), float(eps),
+                                                   _f32(pows, 'pows'), ctr.data_ptr(), self._stream(p)), 'peer_allreduce_yogi')
 
 
 _OPS = None

@@ -60,13 +60,15 @@ class FlatYogi:
     self._ops = _ops_mod.get_ops
     self.params = [p for p in params if p.requires_grad]
     self.lr, self.betas, self.eps = lr, betas, eps
-    n = sum(p.numel() for p in self.params)
+    self.n_params = sum(p.numel() for p in self.params)
+    n = (self.n_params + 3) // 4 * 4             # padded to whole float4s (the pad holds zeros and stays zero)
     p0 = self.params[0]
-    self.flat_p = torch.empty(n, device=p0.device, dtype=p0.dtype)
+    self.flat_p = torch.zeros(n, device=p0.device, dtype=p0.dtype)
     self.flat_g = torch.zeros(n, device=p0.device, dtype=p0.dtype)
     self.m = torch.full((n,), initial_accumulator, device=p0.device, dtype=p0.dtype)
     self.v = torch.full((n,), initial_accumulator, device=p0.device, dtype=p0.dtype)
     self.pows = torch.ones(2, device=p0.device, dtype=p0.dtype)
+    self.peer = None
     o = 0
     with torch.no_grad():
       for p in self.params:
@@ -83,3 +85,41 @@ class FlatYogi:
   def step(self):
     self._ops().yogi_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0], self.betas[1],
                           self.eps, self.pows)
+
+  def enable_peer_allreduce(self, group=None):
+    """Data parallel: allocate this rank's staging buffer in symmetric memory (torch.distributed._symmetric_memory) and
+    exchange the peers' pointers, so that `step_allreduce` can run the gradient all-reduce and the Yogi update as one
+    kernel pair over NVLink peer memory (csrc/peer.cu) instead of an NCCL all-reduce followed by `step`.  Collective:
+    every rank of `group` must call it.  Returns False (and leaves the NCCL route in place) if symmetric memory is not
+    available."""
+    import torch.distributed as dist
+    try:
+      import torch.distributed._symmetric_memory as symm
+      grp = group or dist.group.WORLD
+      nf = self._ops().peer_buffer_floats(self.flat_g.numel())
+      buf = symm.empty(nf, dtype=torch.float32, device=self.flat_g.device)
+      hdl = symm.rendezvous(buf, grp)
+      buf.zero_()
+      torch.cuda.synchronize(self.flat_g.device)
+      dist.barrier(group=group)                     # nobody signals before every rank has cleared its flags
+      ptrs = [int(q) for q in hdl.buffer_ptrs]
+      ok = len(ptrs) == dist.get_world_size(group) and all(ptrs)
+    except Exception as e:                          # no P2P / no symmetric-memory backend on this box
+      import warnings
+      warnings.warn(f'peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL all_reduce + yogi_step')
+      ok = False
+    # the decision must be the same on every rank
+    flag = torch.tensor([1 if ok else 0], device=self.flat_g.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if not int(flag.item()):
+      return False
+    self.peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, rank=dist.get_rank(group),
+                     ctr=torch.zeros(4, dtype=torch.int32, device=self.flat_g.device))
+    return True
+
+  @torch.no_grad()
+  def step_allreduce(self):
+    """flat_g <- sum over ranks; Yogi update with the summed gradient (fused, peer memory)."""
+    pr = self.peer
+    self._ops().peer_allreduce_yogi(pr['ptrs'], pr['rank'], self.flat_g, self.flat_p, self.m, self.v, self.lr,
+                                    self.betas[0], self.betas[1], self.eps, self.pows, pr['ctr'])

@@ -20,14 +20,17 @@ from .optim import FlatYogi
 USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
 GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'
 FUSED_STEP = os.environ.get('VARGP_FUSED_STEP', '1') != '0'
+PEER_ALLREDUCE = os.environ.get('VARGP_PEER_ALLREDUCE', '1') != '0'
 
 
 class ElboStepper:
   def __init__(self, gp, n_data, batch_size, beta=1.0, lr=1e-2, world_size=1, use_graph=True, optimizer=None,
-               shard_factor=None, fused=None):
+               shard_factor=None, fused=None, peer=None):
     """shard_factor: also shard the replicated O(P^3) factor stage over the ranks (elbo.FactorShard); default: on
     when world_size > 1 and the task has at least 512 inducing points per class (below that the three extra
     collectives cost more than the replicated work).
+    peer: data parallel -- gradient all-reduce + Yogi as one kernel pair over NVLink peer memory (csrc/peer.cu) instead
+    of NCCL all_reduce + yogi_step (default: whenever NCCL ranks can map each other's memory).
     fused: take the tape-free value-and-gradient path of `fused_step.FusedElbo` (default: whenever the model is
     eligible -- plain RBF kernel, sampled hypers, ep_var_mean=True); False keeps loss() + autograd."""
     self.gp, self.n_data, self.beta, self.world = gp, n_data, beta, world_size
@@ -47,6 +50,12 @@ class ElboStepper:
     self.graph_nccl = GRAPH_NCCL and world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl'
     if self.shard is not None and not self.graph_nccl:
       use_graph = False                    # collectives inside forward / backward: launch eagerly
+    # gradient all-reduce + Yogi fused over peer memory (csrc/peer.cu) when the optimizer is the flat one and symmetric
+    # memory is available; VARGP_PEER_ALLREDUCE=0 keeps NCCL
+    self.peer = False
+    if ((PEER_ALLREDUCE if peer is None else peer) and world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl' and
+        hasattr(self.opt, 'enable_peer_allreduce')):
+      self.peer = self.opt.peer is not None or self.opt.enable_peer_allreduce()
     self.use_graph = use_graph
     self.graph = None
     dev = next(gp.parameters()).device
@@ -88,6 +97,9 @@ class ElboStepper:
     return terms
 
   def _finish(self):
+    if self.world > 1 and self.peer:
+      self.opt.step_allreduce()          # gradient all-reduce + Yogi as one kernel pair over NVLink peer memory
+      return
     if self.world > 1:
       dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
     self.opt.step()
@@ -145,7 +157,7 @@ class ElboStepper:
     self._restore(snap)
     torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph()
-    self._tail_in_graph = self.world == 1 or self.graph_nccl
+    self._tail_in_graph = self.world == 1 or self.graph_nccl or (bool(self.peer) and self.shard is None)
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._body() if self._tail_in_graph else self._grad_body()
