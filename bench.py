@@ -472,9 +472,12 @@ def run_gpu(args):
     r = cpu_reference_steps(wl if wl != 'scaled' else 'split_mnist', task, 8, 1, budget_s=25.0)
     cpu = dict(value=r['value'], unit='steps/s', cores=r['cores'], kind=r['kind'], sample=r['sample'])
   if world > 1:
-    ctx.dist.destroy_process_group()
+    ctx.barrier()
   if rank != 0:
-    return
+    # (no destroy_process_group: tearing the communicator down after CUDA graphs captured collectives on it can block
+    # at exit; the ranks leave without interpreter teardown once rank 0 has its numbers)
+    sys.stdout.flush()
+    os._exit(0)
 
   pk = peaks()
   is_scaled = wl == 'scaled'
@@ -530,7 +533,10 @@ def run_gpu(args):
                                               tflops=round(d['flops'] / max(d['ms'], 1e-9) / 1e9, 3),
                                               gbs=round(d['bytes'] / max(d['ms'], 1e-9) / 1e6, 1)) for t, d in
                                       sorted(scaled['prof'].items(), key=lambda kv: -kv[1]['ms'])}
-  print(json.dumps(line))
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def run_reference(args):

@@ -1,12 +1,9 @@
 #!/usr/bin/env bash
-# multi-GPU check: scripts/r2_multi.sh <tag> <ngpus>
 set -uo pipefail
-TAG="${1:-r2m}"; N="${2:-2}"; OUT=gpurun_out; mkdir -p $OUT
-timeout 400 python -m pytest tests/test_dist_gpu.py -x -q -m gpu > $OUT/${TAG}_pytest_dist.log 2>&1
-echo "pytest dist rc $?"; tail -4 $OUT/${TAG}_pytest_dist.log
+TAG="${1:-r2m}"; N="${2:-8}"; OUT=gpurun_out; mkdir -p $OUT
 run() { name=$1; shift; extra="$1"; shift
   env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N --steps 50 --warmup 5 $extra > $OUT/${TAG}_bench_n${N}_$name.json 2> $OUT/${TAG}_bench_n${N}_$name.err
-  echo "bench $name rc $?"; python - <<PY
+  echo "rc $?"; python - <<PY
 import json
 try:
   d=json.loads([l for l in open("$OUT/${TAG}_bench_n${N}_$name.json") if l.startswith("{")][-1])
@@ -17,5 +14,4 @@ except Exception as e:
 PY
 }
 run peer "" X=1
-run nccl_graph "--no-scaled" VARGP_PEER_ALLREDUCE=0
 run nccl_eager "--no-scaled" VARGP_PEER_ALLREDUCE=0 VARGP_GRAPH_NCCL=0

@@ -77,17 +77,18 @@ for name, kw in (('graph', dict(C=10, D=784, M=60, t=2, B=128, sigma=10., seed=7
   if 'graph' not in PARTS:
     break
   res = {}
-  for mode in ('eager', 'graph'):
+  # eager: every kernel and collective launched from the host; graph: the default (graph up to the backward pass -- incl.
+  # the factor-shard collectives --, NCCL all_reduce + Yogi behind it); graph_tail: all-reduce + Yogi captured too;
+  # graph_peer: the fused peer-memory all-reduce + Yogi kernels of csrc/peer.cu inside the graph
+  for mode in ('eager', 'graph', 'graph_tail', 'graph_peer'):
     mark(f'part 2 {name} {mode}')
     params, prev, x, y, _ = make_case(**kw)
     gp = util.build_model(params, prev, 3, 10, {}, dev, torch.float32)
     g = torch.Generator().manual_seed(100 + rank)
     xs = torch.rand(4, kw['B'], 784, generator=g).to(dev)
     ys = torch.randint(0, 10, (4, kw['B']), generator=g).to(dev)
-    # eager: NCCL all_reduce + yogi_step launched from the host; graph: one graph launch per step with the fused
-    # peer-memory all-reduce + Yogi kernels (and, factor-sharded, the NCCL all-gathers / reduce-scatters) inside it
     st = ElboStepper(gp, n_data=10 * kw['B'] * world, batch_size=kw['B'], beta=1.7, lr=1e-2, world_size=world,
-                     use_graph=mode == 'graph', peer=None if mode == 'graph' else False)
+                     use_graph=mode != 'eager', peer=mode == 'graph_peer', graph_tail=mode == 'graph_tail')
     torch.manual_seed(11)                       # identical theta draws on every rank
     for i in range(6):
       st.step(xs[i % 4], ys[i % 4])
@@ -99,14 +100,18 @@ for name, kw in (('graph', dict(C=10, D=784, M=60, t=2, B=128, sigma=10., seed=7
     res[mode] = (st.opt.flat_p.clone(), st.terms_vec.clone(), bool(getattr(st, '_tail_in_graph', False)),
                  st.shard is not None)
     out[f'{name}_{mode}_peer_allreduce'] = bool(st.peer)
-  out[f'{name}_param_relerr'] = relerr(res['graph'][0], res['eager'][0])
-  out[f'{name}_terms_relerr'] = relerr(res['graph'][1], res['eager'][1])
-  out[f'{name}_collectives_in_graph'] = res['graph'][2]
+    del st, gp                                  # graphs that hold captured NCCL work must be gone before the group is torn down
+  out[f'{name}_param_relerr'] = max(relerr(res[m][0], res['eager'][0]) for m in ('graph', 'graph_tail', 'graph_peer'))
+  out[f'{name}_terms_relerr'] = max(relerr(res[m][1], res['eager'][1]) for m in ('graph', 'graph_tail', 'graph_peer'))
+  out[f'{name}_collectives_in_graph'] = (not res['graph'][2]) and res['graph_tail'][2] and res['graph_peer'][2]
   out[f'{name}_factor_sharded'] = res['graph'][3]
   # replicas stay in sync: every rank holds the same parameters after the steps
-  p0 = res['graph'][0].clone()
-  dist.broadcast(p0, 0)
-  out[f'{name}_replica_drift'] = relerr(res['graph'][0], p0)
+  drift = 0.0
+  for m in ('graph', 'graph_tail', 'graph_peer'):
+    p0 = res[m][0].clone()
+    dist.broadcast(p0, 0)
+    drift = max(drift, relerr(res[m][0], p0))
+  out[f'{name}_replica_drift'] = drift
 
 mark('checks')
 ok = True
@@ -117,10 +122,20 @@ if 'graph' in PARTS:
   ok = ok and (out['graph_param_relerr'] < 1e-5 and out['graph_sharded_param_relerr'] < 1e-5 and
                out['graph_collectives_in_graph'] and out['graph_sharded_collectives_in_graph'] and
                out['graph_sharded_factor_sharded'] and not out['graph_factor_sharded'] and
-               out['graph_replica_drift'] == 0.0 and out['graph_sharded_replica_drift'] < 1e-6)
+               out['graph_replica_drift'] == 0.0 and out['graph_sharded_replica_drift'] < 1e-6 and
+               out['graph_graph_peer_peer_allreduce'] and not out['graph_graph_peer_allreduce'])
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
+code = 0 if flag.item() == 0 else 1
 if rank == 0:
-  print(json.dumps(dict(world=world, ok=bool(flag.item() == 0), **out)))
-dist.destroy_process_group()
-sys.exit(0 if flag.item() == 0 else 1)
+  print(json.dumps(dict(world=world, ok=code == 0, **out)), flush=True)
+import gc                                                 # noqa: E402
+gc.collect()
+torch.cuda.synchronize()
+dist.barrier()
+mark('done')
+sys.stdout.flush()
+sys.stderr.flush()
+# skip interpreter teardown: destroying the NCCL communicator / symmetric-memory handles after CUDA graphs captured
+# collectives on them can block at exit (observed on the 2-GPU box); everything has been checked and printed
+os._exit(code)

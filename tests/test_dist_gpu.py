@@ -1,6 +1,7 @@
 """Multi-GPU parity under NCCL (one process per GPU, torchrun-spawned): skipped on boxes with fewer than two GPUs.
 See tests/dist_worker_gpu.py for what is asserted (N-rank gradients == 1-rank gradients, replicated and with the
-factor stage sharded; the step graph with the collectives captured == the eager data-parallel step)."""
+factor stage sharded; every data-parallel tail -- graph + eager NCCL tail (default), NCCL captured into the graph, the fused
+peer-memory all-reduce + Yogi kernels -- follows the same trajectory as the fully eager data-parallel step)."""
 import json
 import os
 import socket

@@ -49,8 +49,8 @@ peer_stage_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t npad, co
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(mine);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) m4[i] = g4[i];
-  __threadfence_system();                       // the staged gradient is visible system-wide before the flag is
-  __syncthreads();
+  __threadfence();                              // device scope here; the CTA that publishes the flag adds the system-scope
+  __syncthreads();                              // fence after it has seen every CTA's ticket (fences are cumulative)
   if (threadIdx.x == 0) s_last = atomicAdd(&ctr[1], 1u) == gridDim.x - 1;
   __syncthreads();
   if (s_last) {
@@ -83,35 +83,48 @@ peer_reduce_yogi_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t np
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   float4* g4 = reinterpret_cast<float4*>(gsum);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  // kPU elements per thread and pass: all of their loads (own + every peer's, over NVLink) are issued before the first
+  // use, so a pass costs ONE NVLink round trip instead of one per element
+  constexpr int kPU = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += kPU * stride) {
+    float4 t[kPU][kPeerMax], pp[kPU], mm[kPU], vv[kPU];
 #pragma unroll
-    for (int r = 0; r < kPeerMax; ++r) {
-      if (r < world) {
-        const float4 t = ld_peer4(pb.buf[r] + off + 4 * i);
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    for (int q = 0; q < kPU; ++q) {
+      const int64_t i = i0 + q * stride;
+#pragma unroll
+      for (int r = 0; r < kPeerMax; ++r)
+        if (r < world && i < n4) t[q][r] = ld_peer4(pb.buf[r] + off + 4 * i);
+      if (i < n4) { pp[q] = p4[i]; mm[q] = m4[i]; vv[q] = v4[i]; }
+    }
+#pragma unroll
+    for (int q = 0; q < kPU; ++q) {
+      const int64_t i = i0 + q * stride;
+      if (i >= n4) break;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < kPeerMax; ++r)
+        if (r < world) { s.x += t[q][r].x; s.y += t[q][r].y; s.z += t[q][r].z; s.w += t[q][r].w; }
+      g4[i] = s;
+      const float gs[4] = {s.x, s.y, s.z, s.w};
+      float* pe[4] = {&pp[q].x, &pp[q].y, &pp[q].z, &pp[q].w};
+      float* me[4] = {&mm[q].x, &mm[q].y, &mm[q].z, &mm[q].w};
+      float* ve[4] = {&vv[q].x, &vv[q].y, &vv[q].z, &vv[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gi = gs[e];
+        const float g2 = gi * gi;
+        const float mi = fmaf(b1, *me[e], (1.f - b1) * gi);
+        float vi = *ve[e];
+        const float d = vi - g2;
+        const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        vi = fmaf(-(1.f - b2) * sg, g2, vi);
+        *me[e] = mi;
+        *ve[e] = vi;
+        *pe[e] -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
       }
+      p4[i] = pp[q]; m4[i] = mm[q]; v4[i] = vv[q];
     }
-    g4[i] = s;
-    float4 pp = p4[i], mm = m4[i], vv = v4[i];
-    const float gs[4] = {s.x, s.y, s.z, s.w};
-    float* pe[4] = {&pp.x, &pp.y, &pp.z, &pp.w};
-    float* me[4] = {&mm.x, &mm.y, &mm.z, &mm.w};
-    float* ve[4] = {&vv.x, &vv.y, &vv.z, &vv.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float gi = gs[q];
-      const float g2 = gi * gi;
-      const float mi = fmaf(b1, *me[q], (1.f - b1) * gi);
-      float vi = *ve[q];
-      const float d = vi - g2;
-      const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-      vi = fmaf(-(1.f - b2) * sg, g2, vi);
-      *me[q] = mi;
-      *ve[q] = vi;
-      *pe[q] -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
-    }
-    p4[i] = pp; m4[i] = mm; v4[i] = vv;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -150,8 +163,9 @@ extern "C" int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int
   for (int r = 0; r < world; ++r)
     if (!pb.buf[r] || reinterpret_cast<uintptr_t>(pb.buf[r]) % 16 != 0) return VARGP_ERR_ARG;
   const int64_t n4 = n / 4, npad = n;
-  int64_t blocks = ceil_div(n4, 256);
-  if (blocks > 148) blocks = 148;                      // one resident CTA per SM at most: every CTA spins on the flags
+  int64_t blocks = ceil_div(n4, 256 * 4);
+  if (blocks > 148) blocks = 148;                      // at most one CTA per SM: every CTA spins on the flags
+  if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)stream;
   launch_k(peer_stage_kernel, dim3((unsigned)blocks), dim3(256), 0, s, pb, world, rank, n4, npad, (const float*)flat_g,
            reinterpret_cast<unsigned*>(ctr));

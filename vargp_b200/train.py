@@ -18,19 +18,23 @@ from .dist import shard_coef, shard_loss
 from .optim import FlatYogi
 
 USE_PRIORITY = os.environ.get('VARGP_PRIO', '1') != '0'
-GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'
+GRAPH_NCCL = os.environ.get('VARGP_GRAPH_NCCL', '1') != '0'      # capture the factor-shard collectives (P >= 512) into the step graph
+GRAPH_TAIL = os.environ.get('VARGP_GRAPH_TAIL', '0') != '0'      # N > 1: also capture the gradient all-reduce + Yogi tail
 FUSED_STEP = os.environ.get('VARGP_FUSED_STEP', '1') != '0'
-PEER_ALLREDUCE = os.environ.get('VARGP_PEER_ALLREDUCE', '1') != '0'
+PEER_ALLREDUCE = os.environ.get('VARGP_PEER_ALLREDUCE', '0') != '0'
+NO_ALLREDUCE = os.environ.get('VARGP_NO_ALLREDUCE', '0') != '0'
 
 
 class ElboStepper:
   def __init__(self, gp, n_data, batch_size, beta=1.0, lr=1e-2, world_size=1, use_graph=True, optimizer=None,
-               shard_factor=None, fused=None, peer=None):
+               shard_factor=None, fused=None, peer=None, graph_tail=None):
     """shard_factor: also shard the replicated O(P^3) factor stage over the ranks (elbo.FactorShard); default: on
     when world_size > 1 and the task has at least 512 inducing points per class (below that the three extra
     collectives cost more than the replicated work).
     peer: data parallel -- gradient all-reduce + Yogi as one kernel pair over NVLink peer memory (csrc/peer.cu) instead
-    of NCCL all_reduce + yogi_step (default: whenever NCCL ranks can map each other's memory).
+    of NCCL all_reduce + yogi_step (opt-in: VARGP_PEER_ALLREDUCE=1; measured on par with NCCL at N = 2, behind it at N = 8).
+    graph_tail: N > 1 -- capture the NCCL gradient all-reduce + Yogi step into the step graph as well (opt-in:
+    VARGP_GRAPH_TAIL=1; measured slower than launching them eagerly behind the graph).
     fused: take the tape-free value-and-gradient path of `fused_step.FusedElbo` (default: whenever the model is
     eligible -- plain RBF kernel, sampled hypers, ep_var_mean=True); False keeps loss() + autograd."""
     self.gp, self.n_data, self.beta, self.world = gp, n_data, beta, world_size
@@ -43,15 +47,21 @@ class ElboStepper:
     if shard_factor and world_size > 1 and gp.var_mean_mask == 1.0:
       from .elbo import FactorShard
       self.shard = FactorShard()
-    # N > 1: the gradient all-reduce, the factor-shard collectives and the Yogi step are captured into the step graph
-    # too (NCCL kernels are capturable), so a data-parallel step is ONE graph launch like the single-GPU step.
-    # VARGP_GRAPH_NCCL=0 restores the round-1 split (graph up to the backward pass, eager all-reduce + Yogi; no graph
-    # at all with the factor stage sharded).
-    self.graph_nccl = GRAPH_NCCL and world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl'
+    # N > 1, measured on 2 and 8 B200s at the Split-MNIST shape (profiles/r2_multi_gpu_ab.txt): the fastest tail is the
+    # round-1 one -- the graph ends with the backward pass; NCCL all_reduce and the Yogi step follow eagerly (the host
+    # enqueues them while the graph runs): 1.012 ms/step at N = 2, 1.027 at N = 8, against 0.998 without any exchange.
+    # Capturing the NCCL all-reduce + Yogi into the graph (VARGP_GRAPH_TAIL=1) measured 1.031 (N = 2); the fused
+    # peer-memory all-reduce + Yogi kernel pair of csrc/peer.cu (VARGP_PEER_ALLREDUCE=1, always inside the graph) 1.017
+    # (N = 2) / 1.044 (N = 8: a one-shot all-reduce reads 7 x 1.9 MB over NVLink per rank).  Both stay available and
+    # tested (tests/test_dist_gpu.py); neither is the default.  The factor-shard collectives (P >= 512) ARE captured by
+    # default (VARGP_GRAPH_NCCL=0 restores the round-1 behaviour: no graph at all with the factor stage sharded).
+    nccl = world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl'
+    self.graph_nccl = GRAPH_NCCL and nccl
+    self.graph_tail = (GRAPH_TAIL if graph_tail is None else graph_tail) and nccl
     if self.shard is not None and not self.graph_nccl:
       use_graph = False                    # collectives inside forward / backward: launch eagerly
-    # gradient all-reduce + Yogi fused over peer memory (csrc/peer.cu) when the optimizer is the flat one and symmetric
-    # memory is available; VARGP_PEER_ALLREDUCE=0 keeps NCCL
+    # gradient all-reduce + Yogi fused over peer memory (csrc/peer.cu) when asked for, the optimizer is the flat one and
+    # symmetric memory is available
     self.peer = False
     if ((PEER_ALLREDUCE if peer is None else peer) and world_size > 1 and dist.is_initialized() and dist.get_backend() == 'nccl' and
         hasattr(self.opt, 'enable_peer_allreduce')):
@@ -97,6 +107,9 @@ class ElboStepper:
     return terms
 
   def _finish(self):
+    if NO_ALLREDUCE:                     # measurement only (VARGP_NO_ALLREDUCE=1): ranks step without exchanging gradients
+      self.opt.step()
+      return
     if self.world > 1 and self.peer:
       self.opt.step_allreduce()          # gradient all-reduce + Yogi as one kernel pair over NVLink peer memory
       return
@@ -157,7 +170,7 @@ class ElboStepper:
     self._restore(snap)
     torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph()
-    self._tail_in_graph = self.world == 1 or self.graph_nccl or (bool(self.peer) and self.shard is None)
+    self._tail_in_graph = self.world == 1 or self.graph_tail or bool(self.peer)
     n0 = ops.launch_count()
     with torch.cuda.graph(self.graph, stream=s):
       self.terms = self._body() if self._tail_in_graph else self._grad_body()
