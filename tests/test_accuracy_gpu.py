@@ -133,11 +133,11 @@ def test_end_of_run_accuracy_matches_reference_path(name, cuda_ops):
     tasks, C, D = _toy_tasks(g)
     kw = dict(M=20, steps=300, B=100, lr=3e-2, beta=1.0, log_sigma=math.log(0.5))
   elif name == 'permuted_mnist_shape':   # experiments/vargp.py permuted_mnist: beta=1.64, all classes in every task
-    tasks, C, D = _permuted_tasks(g, n_tasks=3)
-    kw = dict(M=32, steps=120, B=128, lr=1e-2, beta=1.64, log_sigma=math.log(10.))
+    tasks, C, D = _permuted_tasks(g)
+    kw = dict(M=24, steps=80, B=128, lr=1e-2, beta=1.64, log_sigma=math.log(10.))
   else:                              # Split-MNIST shape (D=784, 10 output GPs, 2 classes per task), learned-lengthscale regime
-    tasks, C, D = _mnist_like_tasks(g, n_tasks=4)
-    kw = dict(M=32, steps=150, B=128, lr=1e-2, beta=10.0, log_sigma=math.log(10.))
+    tasks, C, D = _mnist_like_tasks(g)
+    kw = dict(M=20, steps=80, B=128, lr=1e-2, beta=10.0, log_sigma=math.log(10.))
   acc_o, pr_o = _run('oracle', tasks, C, D, **kw)
   acc_g, pr_g = _run('b200', tasks, C, D, **kw)
   print(name, 'oracle acc', [f'{a:.4f}' for a in acc_o], 'b200 acc', [f'{a:.4f}' for a in acc_g],

@@ -13,11 +13,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _bound(ref32, ref64, key=None, base=1e-4, floor=0.0):
-  """max(north-star tolerance, 5 x the reference's own fp32-vs-fp64 error) -- the second term only matters on
-  the ill-conditioned toy cases."""
+  """max(north-star tolerance, 3 x the reference's own fp32-vs-fp64 error) -- the second term only matters on
+  the ill-conditioned toy cases (measured on B200: every quantity of every fixture is within
+  2.0 x the reference's own error, profiles/r2p_parity_report.txt)."""
   a = ref32[key] if key else ref32
   b = ref64[key] if key else ref64
-  return max(base, 5.0 * _err(a, b, floor))
+  return max(base, 3.0 * _err(a, b, floor))
 
 
 def _err(a, b, floor=0.0):

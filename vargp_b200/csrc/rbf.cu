@@ -1,6 +1,8 @@
 // ARD-RBF kernel: operand scaling / norms (forward) and the adjoint passes that turn Kbar into
 // gradients for z, x and theta.  All of these are streaming (HBM / L2 bound) SIMT kernels; the only
 // dense contractions of the RBF path (x.z^T forward, W.X backward) are GEMMs (gemm_simt.cu / gemm_tc.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vargp {
@@ -447,7 +449,9 @@ extern "C" int vargp_rbf_bwd_prep(float* Kbar, const float* K, int64_t H, int64_
   if (dsum && Pa != Pb) return VARGP_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t G = H * C;
-  {   // narrow matrices: warp-per-row kernel (no memset, no row-sum atomics)
+  static int rows_on = -1;
+  if (rows_on < 0) { const char* e = getenv("VARGP_RBF_ROWS"); rows_on = e ? atoi(e) : 1; }
+  if (rows_on) {   // narrow matrices: warp-per-row kernel (no memset, no row-sum atomics)
     const bool a16 = ((reinterpret_cast<uintptr_t>(Kbar) | reinterpret_cast<uintptr_t>(K)) % 16 == 0) && Pb % 4 == 0;
     const int64_t cap = 32 * kRowsK * (a16 ? 4 : 1);
     if (Pb <= cap && ceil_div(Pa, 32) <= 65535 && G * Pa * Pb <= (int64_t)64 << 20) {
@@ -484,7 +488,9 @@ extern "C" int vargp_rbf_bwd_finish(const float* zs, const float* Gz1, const flo
   if (!zs || !theta || !Zbar || !theta_bar) return VARGP_ERR_ARG;
   if ((Gz1 != nullptr) != (r1 != nullptr) || (Gz2 != nullptr) != (r2 != nullptr)) return VARGP_ERR_ARG;
   const int64_t R = C * P;
-  {
+  static int v4_on = -1;
+  if (v4_on < 0) { const char* e = getenv("VARGP_RBF_FIN4"); v4_on = e ? atoi(e) : 1; }
+  if (v4_on) {
     uintptr_t bits = reinterpret_cast<uintptr_t>(zs) | reinterpret_cast<uintptr_t>(Zbar);
     if (Gz1) bits |= reinterpret_cast<uintptr_t>(Gz1);
     if (Gz2) bits |= reinterpret_cast<uintptr_t>(Gz2);
