@@ -23,13 +23,17 @@ class EmuOps:
     dst.copy_(src.unsqueeze(0) * torch.exp(-theta[:, :D]).unsqueeze(1))
     norms.copy_((dst * dst).sum(-1))
 
-  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag=None, sm_limit=0):
+  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag=None, sm_limit=0, c_tri=None):
     g2 = torch.exp(2. * theta[:, -1]).view(-1, 1, 1, 1)
     dot = a @ b.transpose(-1, -2)
     val = g2 * torch.exp(dot - 0.5 * an.unsqueeze(-1) - 0.5 * bn.unsqueeze(-2))
     if sym:
       eye = torch.eye(a.shape[-2], dtype=torch.bool, device=a.device)
       val = torch.where(eye, g2.expand_as(val), val)
+    if c_tri == 'lower':                 # contract: the other triangle is zero-filled
+      val = torch.tril(val)
+    elif c_tri == 'upper':
+      val = torch.triu(val)
     out.copy_(val)
 
   def gemm(self, A, B, C, alpha=1., beta=0., a_tri=None, b_tri=None, c_tri=None, tag=None, zeroed=False, sm_limit=0):

@@ -53,6 +53,7 @@ STACK_CLASSES = os.environ.get('VARGP_STACK_CLASSES', '1') != '0'
 V_SIDE = os.environ.get('VARGP_V_SIDE', '1') != '0'
 # VARGP_WHITEN=0: the per-task-block products through the batched GEMMs even when M fits the shared-memory kernels
 USE_WHITEN = os.environ.get('VARGP_WHITEN', '1') != '0'
+KZZ_LOWER = os.environ.get('VARGP_KZZ_LOWER', '1') != '0'
 # SMs the persistent Kzx GEMM may occupy while it runs beside Kzz -> Cholesky (148 - H*C - a margin at the benched shape)
 SIDE_SM_LIMIT = int(os.environ.get('VARGP_SIDE_SM_LIMIT', '112'))
 
@@ -100,6 +101,19 @@ class _Fork:
   def join(self):
     if self.side is not None:
       torch.cuda.current_stream().wait_stream(self.side)
+
+  def side_event(self):
+    """Event marking what has been queued on the side stream so far (None without a side stream)."""
+    if self.side is None:
+      return None
+    ev = torch.cuda.Event()
+    ev.record(self.side)
+    return ev
+
+  @staticmethod
+  def main_wait(ev):
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
 
   def after_main(self):
     """Make what is queued on the side stream from now on also wait for everything queued on the current stream."""
@@ -272,7 +286,9 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
   for (h0, h1, c0, c1) in rects:
     r = (slice(h0, h1), slice(c0, c1))
     th, Hs, Cs = theta[h0:h1], h1 - h0, c1 - c0
-    ops.rbf_gram(zs4[r], zn3[r], zs4[r], zn3[r], th, Kzz[r], True, tag='Kzz')
+    # the factorisation reads the lower triangle only: a third fewer tiles on the head of the critical chain; the backward
+    # pass, which needs the full symmetric Gram, mirrors it on its side branch (marginal_backward)
+    ops.rbf_gram(zs4[r], zn3[r], zs4[r], zn3[r], th, Kzz[r], True, tag='Kzz', c_tri='lower' if KZZ_LOWER else None)
     # W = chol(Kzz + eps I)^-1                                                 [gp_utils.py:5-11]
     ops.chol_inv(Kzz[r], L[r], W[r], JITTER, info.view(H, C)[r].reshape(-1) if Hs * Cs == G else
                  info[h0 * C + c0:h0 * C + c1])
@@ -328,6 +344,7 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     ctx.shard, ctx.part = shard, (k, g0, g1, slots)
     ctx.saved = dict(theta=theta, zs=zs4, xs=xs, Kzz=Kzz, Kzx=Kzx, W=W, T=T, nu=nu, V=V, NV=NV,
                      m_all=m_all, Lu_all=Lu_all)
+    ctx.kzz_lower = KZZ_LOWER
   return f_mean, f_var, kl, info, L
 
 
@@ -358,7 +375,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
   Wbarf, Gf, nubarf, Tbar, theta_bar, r1z, csumz = _zeros_many(dev, dt, (slots, P, P), (slots, P, P), (slots, P),
                                                                (H, C, S, M, M), (H, D + 1), (H, C, P), (H, B))
   Wbar, Gm, nubar = Wbarf[:G].view(H, C, P, P), Gf[:G].view(H, C, P, P), nubarf[:G].view(H, C, P)
-  Kxbar = Gz1 = Gx = r1 = csum = None
+  Kxbar = Gz1 = Gx = r1 = csum = kzz_ready = None
   fork = _Fork(dev)
   have_data = g_mean is not None or g_var is not None
   if have_data:
@@ -375,6 +392,10 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
     Gx = new(H, C, B, D) if need_x_grad else None
     r1, csum = r1z, csumz
     with fork:
+      if getattr(ctx, 'kzz_lower', False):       # complete the symmetric Gram (its forward pass only formed the lower triangle)
+        for (h0, h1, c0, c1) in rects:
+          ops.sym_phi(Kzz[h0:h1, c0:c1], mirror=True)
+        kzz_ready, ctx.kzz_lower = fork.side_event(), False
       ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
       if STACK_CLASSES:
@@ -450,6 +471,9 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
     Kzzbar = X[r]                                                # Xi is dead after Y: reuse its storage
     ops.gemm(W[r].transpose(-1, -2), Y[r], Kzzbar, alpha=-1., a_tri='upper', tag='Kzzbar=-Wt*Y', zeroed=True)
     # RBF adjoint of the Kzz side                                                
+    if getattr(ctx, 'kzz_lower', False):         # no side branch ran (no data term): mirror here
+      ops.sym_phi(Kzz[r], mirror=True)
+    _Fork.main_wait(kzz_ready)
     ops.rbf_bwd_prep(Kzzbar, Kzz[r], r2[r], None, dg[r])          # Kzzbar <- Kzzbar * Kzz (diag -> dg) ; row sums
     ops.gemm(Kzzbar, zs[r], Gz2[r], tag='Gz2=Wk2*zs')
   if last_raw:

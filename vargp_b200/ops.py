@@ -283,8 +283,9 @@ class CudaOps:
     d.sm_limit = int(sm_limit)
     self._run_gemm(d, C, tag, zeroed)
 
-  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram', sm_limit=0):
-    """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}."""
+  def rbf_gram(self, a, an, b, bn, theta, out, sym, tag='rbf_gram', sm_limit=0, c_tri=None):
+    """out[h,c] = gamma2[h] exp(a b^T - |a|^2/2 - |b|^2/2); a (H,C,Pa,D), b (H,Cb,Pb,D), Cb in {1, C}.
+    c_tri='lower': only the lower triangle of a symmetric Gram is formed (a third fewer tiles); complete it with sym_phi(mirror)."""
     _f32(theta, 'theta', contiguous=False)
     d, nb = self._desc(a, b.transpose(-1, -2), out, 1., 0., None, None, None)
     _f32(an, 'an', contiguous=False)
@@ -303,6 +304,7 @@ class CudaOps:
     d.e_theta_bs = (i64 * 3)(*_bstrides(th, nb))
     d.e_D = theta.shape[1] - 1
     d.sm_limit = int(sm_limit)
+    d.tri_c = _TRI[c_tri]               # symmetric Gram: only that triangle is computed (the other is zero-filled)
     self._run_gemm(d, out, tag)
 
   # -- RBF operand prep / adjoint -------------------------------------------------------------
