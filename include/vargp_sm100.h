@@ -132,6 +132,21 @@ int vargp_chol_inv_mid(const float* A, int64_t a_ld, int64_t a_bs, float* L, int
                        float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                        int32_t* info, void* stream);
 int64_t vargp_chol_mid_config(int64_t max_n);
+/* Cluster-cooperative variant for 32 < n <= 320 (one thread-block cluster of 2 or 4 CTAs per matrix, block rows dealt
+ * round-robin to the CTAs' shared memory, panels and rows of the inverse pushed through distributed shared memory, the
+ * inverse formed during the factorisation sweep; potrf_cluster.cu): what vargp_chol_inv takes by default at the
+ * Split-MNIST sizes (P = 60 ... 300).  A may alias L or W; L and W must differ.  Replaces var_gp/gp_utils.py:5-11 plus the
+ * solves of :89-92,124-134,175-182 in ONE launch.
+ * vargp_chol_cluster_config: routing window [min_n, max_n] of vargp_chol_inv (0, 0 disables; negative only queries),
+ * returns the previous (min_n << 32) | max_n.  vargp_chol_cluster_wants: 1 if vargp_chol_inv would route n there. */
+int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                           float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                           int32_t* info, void* stream);
+int64_t vargp_chol_cluster_config(int64_t min_n, int64_t max_n);
+int vargp_chol_cluster_wants(int64_t n);
+/* profiling aid: clock64 stamps of the phases of matrix 0 (per CTA rank and block step) into a device buffer of
+ * 4 * 16 * 16 int64 (scripts/chol_stamps.py); NULL turns it off. */
+void vargp_chol_cluster_debug(void* buf);
 /* block size (multiple of 32; 0 keeps it) and minimum n (< 0 keeps it) of the blocked path;
  * returns (min_n << 32) | block after the update. */
 int64_t vargp_chol_config(int64_t block, int64_t min_n);

@@ -11,14 +11,15 @@ ns = [int(a) for a in sys.argv[1:]] or [60, 120, 128, 180, 240, 300, 320]
 for n in ns:
   g = torch.Generator().manual_seed(n)
   X = torch.randn(30, n, n + 5, generator=g, dtype=torch.float64)
-  A = (X @ X.transpose(-1, -2) / (n + 5) + 0.05 * torch.eye(n, dtype=torch.float64)).float().cuda()
+  A64 = X @ X.transpose(-1, -2) / (n + 5) + 0.05 * torch.eye(n, dtype=torch.float64)
+  L64 = torch.linalg.cholesky(A64 + 1e-4 * torch.eye(n, dtype=torch.float64))
+  A = A64.float().cuda()
   L, W = torch.empty_like(A), torch.empty_like(A)
   info = torch.zeros(30, device='cuda', dtype=torch.int32)
   res = {}
-  for route, mid in (('mid', 320), ('default_r1', 0)):
+  for route, mid, cl in (('cluster', 0, (33, 320)), ('mid', 320, (0, 0)), ('blocked_or_small', 0, (0, 0))):
     old = ops.chol_mid_config(mid)
-    if route == 'mid':
-      os.environ.pop('X', None)
+    old_cl = ops.chol_cluster_config(*cl)
     for _ in range(5):
       ops.chol_inv(A, L, W, 1e-4, info)
     torch.cuda.synchronize()
@@ -29,5 +30,7 @@ for n in ns:
     e1.record()
     torch.cuda.synchronize()
     res[route] = round(e0.elapsed_time(e1) / 20 * 1e3, 1)
+    res[route + '_err'] = float(f'{((L.double().cpu() - L64).norm() / L64.norm()).item():.2e}')
     ops.chol_mid_config(old)
-  print(json.dumps(dict(n=n, batch=30, us=res)))
+    ops.chol_cluster_config(*old_cl)
+  print(json.dumps(dict(n=n, batch=30, us=res)), flush=True)

@@ -146,14 +146,21 @@ def test_chol_reports_non_pd(cuda_ops):
                                         (300, 6, 0), (129, 3, 128), (1000, 2, 256), (300, 30, 128), (128, 5, 128),
                                         (60, 30, 128), (97, 3, 128), (1, 2, 128), (33, 4, 128), (20, 7, 128),
                                         (300, 30, 'mid'), (129, 3, 'mid'), (160, 4, 'mid'), (200, 5, 'mid'), (257, 2, 'mid'),
-                                        (320, 3, 'mid'), (180, 33, 'mid')])
+                                        (320, 3, 'mid'), (180, 33, 'mid'),
+                                        (300, 30, 'cluster'), (33, 3, 'cluster'), (60, 30, 'cluster'), (64, 2, 'cluster'),
+                                        (65, 2, 'cluster'), (96, 5, 'cluster'), (97, 4, 'cluster'), (120, 30, 'cluster'),
+                                        (128, 7, 'cluster'), (129, 3, 'cluster'), (180, 30, 'cluster'), (200, 5, 'cluster'),
+                                        (240, 30, 'cluster'), (257, 2, 'cluster'), (289, 40, 'cluster'), (320, 3, 'cluster')])
 def test_chol_inv_blocked(cuda_ops, n, batch, nb):
   """vargp_chol_inv: GEMM-driven blocked factorisation + inverse (potrf_blocked.cu) incl. ragged block counts;
   nb = 0 is the small-matrix route through the one-CTA kernels."""
   old = cuda_ops.chol_config()
   old_mid = cuda_ops.chol_mid_config(320 if nb == 'mid' else 0)      # the blocked cases keep the blocked route at n <= 320
+  old_cl = cuda_ops.chol_cluster_config(*((33, 320) if nb == 'cluster' else (0, 0)))   # potrf_cluster.cu only where asked
   try:
-    if nb == 'mid':
+    if nb == 'cluster':
+      assert cuda_ops.chol_cluster_wants(n)
+    elif nb == 'mid':
       pass
     elif nb:
       cuda_ops.chol_config(nb, nb + 1)
@@ -185,6 +192,42 @@ def test_chol_inv_blocked(cuda_ops, n, batch, nb):
   finally:
     cuda_ops.chol_config(*old)
     cuda_ops.chol_mid_config(old_mid)
+    cuda_ops.chol_cluster_config(*old_cl)
+
+
+def test_chol_inv_cluster_reports_first_bad_pivot(cuda_ops):
+  """potrf_cluster.cu: the first failing pivot over all CTAs of the cluster is reported, good matrices are untouched by bad ones."""
+  n = 300
+  A = torch.eye(n, dtype=torch.float64).repeat(4, 1, 1)
+  A[1, 170, 170] = -1.0
+  A[1, 250, 250] = -1.0
+  A[2, 3, 3] = -2.0
+  A[3, 299, 299] = -1.0
+  L, W = torch.empty(4, n, n, device='cuda'), torch.empty(4, n, n, device='cuda')
+  info = torch.full((4,), -7, device='cuda', dtype=torch.int32)
+  old = cuda_ops.chol_cluster_config(33, 320)
+  try:
+    cuda_ops.chol_inv(dev(A), L, W, 1e-4, info)
+  finally:
+    cuda_ops.chol_cluster_config(*old)
+  assert info.tolist() == [0, 171, 4, 300]
+  assert torch.allclose(L[0], torch.eye(n, device='cuda') * (1 + 1e-4) ** 0.5)
+
+
+def test_chol_inv_cluster_in_place(cuda_ops):
+  """A may alias W (the blocked driver's calling convention for diagonal blocks)."""
+  n, batch = 250, 6
+  X = rnd(batch, n, n + 5, seed=77)
+  A = X @ X.transpose(-1, -2) / (n + 5) + 0.05 * torch.eye(n, dtype=torch.float64)
+  L64 = torch.linalg.cholesky(A + 1e-4 * torch.eye(n, dtype=torch.float64))
+  W64 = torch.linalg.solve_triangular(L64, torch.eye(n, dtype=torch.float64).expand(batch, n, n), upper=False)
+  W = dev(A)
+  L = torch.empty_like(W)
+  info = torch.zeros(batch, device='cuda', dtype=torch.int32)
+  cuda_ops.chol_inv_cluster(W, L, W, 1e-4, info)
+  assert int(info.abs().max()) == 0
+  close(L, L64, 2e-5, 'chol')
+  close(W, W64, 3e-5, 'inverse')
 
 
 def test_chol_inv_mid_reports_first_bad_pivot(cuda_ops):
@@ -196,16 +239,19 @@ def test_chol_inv_mid_reports_first_bad_pivot(cuda_ops):
   L, W = torch.empty(3, n, n, device='cuda'), torch.empty(3, n, n, device='cuda')
   info = torch.zeros(3, device='cuda', dtype=torch.int32)
   old = cuda_ops.chol_mid_config(320)
+  old_cl = cuda_ops.chol_cluster_config(0, 0)
   try:
     cuda_ops.chol_inv(dev(A), L, W, 1e-4, info)
   finally:
     cuda_ops.chol_mid_config(old)
+    cuda_ops.chol_cluster_config(*old_cl)
   assert info.tolist() == [0, 171, 4]
 
 
 def test_chol_inv_blocked_reports_first_bad_pivot(cuda_ops):
   old = cuda_ops.chol_config()
   old_mid = cuda_ops.chol_mid_config(0)
+  old_cl = cuda_ops.chol_cluster_config(0, 0)
   try:
     cuda_ops.chol_config(64, 65)
     n = 300
@@ -220,6 +266,7 @@ def test_chol_inv_blocked_reports_first_bad_pivot(cuda_ops):
   finally:
     cuda_ops.chol_config(*old)
     cuda_ops.chol_mid_config(old_mid)
+    cuda_ops.chol_cluster_config(*old_cl)
 
 
 def test_chol_strided_block_view(cuda_ops):

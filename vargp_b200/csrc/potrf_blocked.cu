@@ -30,6 +30,11 @@ extern "C" int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, 
                                     float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                                     int32_t* info, int64_t info_base, int accumulate, void* stream);
 
+extern "C" int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                                      float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                                      int32_t* info, void* stream);
+extern "C" int vargp_chol_cluster_wants(int64_t n);
+
 namespace vargp {
 
 constexpr int kInitRows = 8;       // rows per CTA of the two passes below (one row per CTA was launch-bound)
@@ -126,6 +131,8 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     e = getenv("VARGP_CHOL_MID_MIN_N");
     if (e) g_mid_min_n = atoi(e);
   }
+  if (vargp_chol_cluster_wants(n))                          // one cluster of 2 / 4 CTAs per matrix (potrf_cluster.cu)
+    return vargp_chol_inv_cluster(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
   if (n >= g_mid_min_n && n <= g_mid_max_n && A != L)      // whole matrix resident in one CTA (potrf_mid.cu)
     return vargp_chol_inv_mid(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
   const int nb = g_blk_nb;

@@ -70,6 +70,10 @@ def _load():
   lib.vargp_chol_mid_config.restype = i64
   lib.vargp_chol_config.argtypes = [i64, i64]
   lib.vargp_chol_config.restype = i64
+  lib.vargp_chol_cluster_config.argtypes = [i64, i64]
+  lib.vargp_chol_cluster_config.restype = i64
+  lib.vargp_chol_cluster_wants.argtypes = [i64]
+  lib.vargp_chol_inv_cluster.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_tril_unpack.argtypes = [vp, i64, i64, vp, vp]
   lib.vargp_tril_unpack_bwd.argtypes = [vp, vp, i64, i64, vp, vp]
   lib.vargp_kl_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp]
@@ -398,6 +402,25 @@ class CudaOps:
   def chol_mid_config(self, max_n=-1):
     """Largest n that vargp_chol_inv routes to the whole-matrix shared-memory kernel (0 disables); returns the previous value."""
     return int(self.lib.vargp_chol_mid_config(int(max_n)))
+
+  def chol_cluster_config(self, min_n=-1, max_n=-1):
+    """Routing window [min_n, max_n] of the cluster-cooperative kernel (potrf_cluster.cu; 0, 0 disables, negative only
+    queries); returns the previous (min_n, max_n)."""
+    r = int(self.lib.vargp_chol_cluster_config(int(min_n), int(max_n)))
+    return r >> 32, r & 0xffffffff
+
+  def chol_inv_cluster(self, K, L, W, jitter, info):
+    """The cluster-cooperative kernel directly (32 < n <= 320); K may alias L or W."""
+    ap, ald, abs_, n, batch = self._mat_batch(K, 'K')
+    lp, lld, lbs, n2, batch2 = self._mat_batch(L, 'L')
+    wp, wld, wbs, n3, batch3 = self._mat_batch(W, 'W')
+    if not ((n, batch) == (n2, batch2) == (n3, batch3)) or info.numel() != batch or info.dtype != torch.int32:
+      raise VargpError('chol_inv_cluster: shape mismatch')
+    self._check(self.lib.vargp_chol_inv_cluster(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
+                                                info.data_ptr(), self._stream(L)), 'chol_inv_cluster')
+
+  def chol_cluster_wants(self, n):
+    return bool(self.lib.vargp_chol_cluster_wants(int(n)))
 
   def chol_config(self, block=0, min_n=-1):
     """Set block size / minimum n of the blocked factorisation; returns (block, min_n) in effect."""
