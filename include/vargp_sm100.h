@@ -142,13 +142,19 @@ int64_t vargp_chol_mid_config(int64_t max_n);
 int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                            float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                            int32_t* info, void* stream);
+/* same with the pivot reporting of vargp_chol_ex (info_base / accumulate): the diagonal-block step of the blocked
+ * factorisation for block sizes 129 ... 320 (vargp_chol_config block = 256). */
+int vargp_chol_inv_cluster_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                              float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                              int32_t* info, int64_t info_base, int accumulate, void* stream);
 int64_t vargp_chol_cluster_config(int64_t min_n, int64_t max_n);
 int vargp_chol_cluster_wants(int64_t n);
 /* profiling aid: clock64 stamps of the phases of matrix 0 (per CTA rank and block step) into a device buffer of
  * 4 * 16 * 16 int64 (scripts/chol_stamps.py); NULL turns it off. */
 void vargp_chol_cluster_debug(void* buf);
-/* block size (multiple of 32; 0 keeps it) and minimum n (< 0 keeps it) of the blocked path;
- * returns (min_n << 32) | block after the update. */
+/* block size (multiple of 32; 0 keeps it; 1 = automatic: 256 with the diagonal blocks on vargp_chol_inv_cluster_ex, 128 on
+ * vargp_chol_inv_small when the cluster kernel is disabled) and minimum n (< 0 keeps it) of the blocked path;
+ * returns (min_n << 32) | block after the update (block = 1 while automatic). */
 int64_t vargp_chol_config(int64_t block, int64_t min_n);
 
 /* packed row-major lower triangle -> (C, M, M) with softplus on the diagonal, and its adjoint.

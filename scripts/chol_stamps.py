@@ -33,5 +33,6 @@ for r in range(4):
   for k in range(nblk):
     f = lambda s: (int(b[r, k, s]) - t0) / GHZ / 1e3 if int(b[r, k, s]) else float('nan')
     print(f'  k={k}: sync1 {f(0):7.2f} | B done w0 {f(1):7.2f} w1 {f(5):7.2f} | sync2 {f(2):7.2f} | C done w0 {f(3):7.2f} w1 {f(7):7.2f}'
-          f' | diag start {f(8):7.2f} factored {f(9):7.2f} inverted {f(10):7.2f} pushed {f(11):7.2f}')
+          f' | diag start {f(8):7.2f} factored {f(9):7.2f} inverted {f(10):7.2f} pushed {f(11):7.2f}'
+          f' | B(w0): item start {f(12):7.2f} product {f(13):7.2f} staged {f(14):7.2f}')
   print(f'  final sync {(int(b[r, 15, 14]) - t0) / GHZ / 1e3:7.2f}  end {(int(b[r, 15, 15]) - t0) / GHZ / 1e3:7.2f}')

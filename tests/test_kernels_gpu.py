@@ -150,15 +150,20 @@ def test_chol_reports_non_pd(cuda_ops):
                                         (300, 30, 'cluster'), (33, 3, 'cluster'), (60, 30, 'cluster'), (64, 2, 'cluster'),
                                         (65, 2, 'cluster'), (96, 5, 'cluster'), (97, 4, 'cluster'), (120, 30, 'cluster'),
                                         (128, 7, 'cluster'), (129, 3, 'cluster'), (180, 30, 'cluster'), (200, 5, 'cluster'),
-                                        (240, 30, 'cluster'), (257, 2, 'cluster'), (289, 40, 'cluster'), (320, 3, 'cluster')])
+                                        (240, 30, 'cluster'), (257, 2, 'cluster'), (289, 40, 'cluster'), (320, 3, 'cluster'),
+                                        (1000, 3, 'cluster256'), (600, 4, 'cluster256'), (2048, 2, 'cluster256'),
+                                        (700, 2, 'cluster320')])
 def test_chol_inv_blocked(cuda_ops, n, batch, nb):
   """vargp_chol_inv: GEMM-driven blocked factorisation + inverse (potrf_blocked.cu) incl. ragged block counts;
   nb = 0 is the small-matrix route through the one-CTA kernels."""
   old = cuda_ops.chol_config()
   old_mid = cuda_ops.chol_mid_config(320 if nb == 'mid' else 0)      # the blocked cases keep the blocked route at n <= 320
-  old_cl = cuda_ops.chol_cluster_config(*((33, 320) if nb == 'cluster' else (0, 0)))   # potrf_cluster.cu only where asked
+  cl = isinstance(nb, str) and nb.startswith('cluster')
+  old_cl = cuda_ops.chol_cluster_config(*((33, 320) if cl else (0, 0)))   # potrf_cluster.cu only where asked
   try:
-    if nb == 'cluster':
+    if cl and len(nb) > 7:            # blocked driver with cluster-factored diagonal blocks of 256 / 320
+      cuda_ops.chol_config(int(nb[7:]), int(nb[7:]) + 1)
+    elif nb == 'cluster':
       assert cuda_ops.chol_cluster_wants(n)
     elif nb == 'mid':
       pass

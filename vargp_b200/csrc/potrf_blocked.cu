@@ -34,6 +34,9 @@ extern "C" int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs
                                       float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                                       int32_t* info, void* stream);
 extern "C" int vargp_chol_cluster_wants(int64_t n);
+extern "C" int vargp_chol_inv_cluster_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                                         float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                                         int32_t* info, int64_t info_base, int accumulate, void* stream);
 
 namespace vargp {
 
@@ -74,7 +77,9 @@ zero_upper_kernel(float* __restrict__ L, int64_t ld, int64_t bs, int n, int nb) 
   }
 }
 
-static int g_blk_nb = 128;        // diagonal block size of the blocked factorisation
+static int g_blk_nb = 0;          // diagonal block size of the blocked factorisation; 0 = auto: 256 when the cluster kernel
+                                  // (potrf_cluster.cu) takes the diagonal blocks, else 128 (potrf_small.cu).  Measured (B200,
+                                  // batch 30, us): n=500: 455 -> 320; 1000: 1178 -> 920; 2048: 3642 -> 2785
 static bool g_no_small = false;   // VARGP_CHOL_NO_SMALL=1: diagonal blocks through the chol.cu kernels (A/B timing)
 static int g_blk_min_n = 129;     // matrices at least this large take the blocked path (n <= 128: potrf_small.cu)
 static int g_mid_max_n = 192;     // 128 < n <= this: whole matrix in one CTA's shared memory (potrf_mid.cu); 0 disables.
@@ -99,9 +104,10 @@ static vargp_gemm_t gemm_desc(int64_t batch) {
 using namespace vargp;
 
 extern "C" int64_t vargp_chol_config(int64_t block, int64_t min_n) {
+  if (block == 1) g_blk_nb = 0;                                   // 1 = auto (reported as 1, so that a query can be restored)
   if (block >= 32 && block <= 1024 && block % 32 == 0) g_blk_nb = (int)block;
   if (min_n >= 0) g_blk_min_n = (int)min_n;
-  return ((int64_t)g_blk_min_n << 32) | (int64_t)g_blk_nb;
+  return ((int64_t)g_blk_min_n << 32) | (int64_t)(g_blk_nb ? g_blk_nb : 1);
 }
 
 extern "C" int64_t vargp_chol_mid_config(int64_t max_n) {
@@ -135,7 +141,7 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     return vargp_chol_inv_cluster(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
   if (n >= g_mid_min_n && n <= g_mid_max_n && A != L)      // whole matrix resident in one CTA (potrf_mid.cu)
     return vargp_chol_inv_mid(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
-  const int nb = g_blk_nb;
+  const int nb = g_blk_nb ? g_blk_nb : (vargp_chol_cluster_wants(256) ? 256 : 128);
   if (n <= 128 && !g_no_small)       // whole matrix fits the shared-memory kernel
     return vargp_chol_inv_small(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, 0, 0, stream);
   if (n < g_blk_min_n || n <= nb) {
@@ -166,7 +172,12 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     }
     // (ii) diagonal block factor (first failing pivot of the whole matrix wins) and (iii) its inverse, in place of
     //      the consumed block of W: one shared-memory kernel for blocks up to 128, else the one-CTA kernels
-    if (kb <= 128 && !g_no_small) {
+    if (kb > 128 && kb <= 320 && vargp_chol_cluster_wants(kb) && !g_no_small) {
+      // one cluster per diagonal block (potrf_cluster.cu), in place of the consumed block of W
+      rc = vargp_chol_inv_cluster_ex(Wkk, w_ld, w_bs, Lkk, l_ld, l_bs, Wkk, w_ld, w_bs, kb, batch, 0.f, info, k0,
+                                     k0 > 0 ? 1 : 0, stream);
+      if (rc) return rc;
+    } else if (kb <= 128 && !g_no_small) {
       rc = vargp_chol_inv_small(Wkk, w_ld, w_bs, Lkk, l_ld, l_bs, Wkk, w_ld, w_bs, kb, batch, 0.f, info, k0,
                                 k0 > 0 ? 1 : 0, stream);
       if (rc) return rc;

@@ -220,7 +220,7 @@ template <int CS>
 __global__ void __launch_bounds__(kClThreads, 1)
 potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_bs, float* __restrict__ Lout, int64_t l_ld,
                          int64_t l_bs, float* __restrict__ Wout, int64_t w_ld, int64_t w_bs, int n, float jitter,
-                         int32_t* __restrict__ info, int maxblk, long long* dbg) {
+                         int32_t* __restrict__ info, int info_base, int accumulate, int maxblk, long long* dbg) {
   pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -315,12 +315,15 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
         if (u < nrow) {                                            // panel block of row i: L_ik = A_ik D_k^T
           const int i = i0 + u * CS;
           float* Lik = Lst + (rowoff(i) + k) * BLK;
+          if (wid == 0) CL_STAMP(12);
           mk_zero<R>(acc);
           mk_fma_rowA<R>(acc, Lik + rr * BLD, DT + c0);
           __syncwarp();
+          if (wid == 0) CL_STAMP(13);
           mk_store<R>(Lik + rr * BLD + c0, acc);
           mk_store_t<R>(slots + i * BLK + c0 * BLD + rr, acc);     // slot i = L_ik^T
           unit_sync();
+          if (wid == 0) CL_STAMP(14);
           push(i, [&](int q) { return lastrow(q) >= i; });
         } else {                                                   // row k of the inverse: W_kj = D_k X_kj
           const int j = u - nrow;
@@ -408,7 +411,8 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
       const int v = (q == 0) ? *s_info : *cluster.map_shared_rank(s_info, q);
       if (v && (best == 0 || v < best)) best = v;
     }
-    info[mat] = best;
+    if (!accumulate) info[mat] = best ? best + info_base : 0;
+    else if (best && info[mat] == 0) info[mat] = best + info_base;
   }
   float* L = Lout + (int64_t)mat * l_bs;
   float* W = Wout + (int64_t)mat * w_bs;
@@ -435,8 +439,8 @@ static int g_cl_min_n = 33, g_cl_max_n = 320;        // vargp_chol_inv routes mi
 
 template <int CS>
 static int launch_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs, float* W,
-                          int64_t w_ld, int64_t w_bs, int n, int64_t batch, float jitter, int32_t* info,
-                          cudaStream_t stream) {
+                          int64_t w_ld, int64_t w_bs, int n, int64_t batch, float jitter, int32_t* info, int info_base,
+                          int accumulate, cudaStream_t stream) {
   const int nblk = (n + CB - 1) / CB;
   int maxblk = 0;
   for (int q = 0; q < CS; ++q) {
@@ -465,7 +469,7 @@ static int launch_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, potrf_inv_cluster_kernel<CS>, A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, jitter, info,
-                     maxblk, g_cl_dbg);
+                     info_base, accumulate, maxblk, g_cl_dbg);
   return launch_status();
 }
 
@@ -499,13 +503,21 @@ extern "C" int vargp_chol_cluster_wants(int64_t n) {
 
 // L = chol(A + jitter I), W = L^-1 for 32 < n <= 320 on one cluster per matrix.  A may alias L or W (a CTA reads its block
 // rows completely before anybody stores); L and W must differ.
-extern "C" int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
-                                      float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
-                                      int32_t* info, void* stream) {
+extern "C" int vargp_chol_inv_cluster_ex(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                                         float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                                         int32_t* info, int64_t info_base, int accumulate, void* stream) {
   if (!A || !L || !W || n < 1 || batch < 1 || a_ld < n || l_ld < n || w_ld < n || L == W) return VARGP_ERR_ARG;
   if (n <= CB || n > 320 || batch > (1 << 20)) return VARGP_ERR_UNSUPPORTED;
   const int nblk = (int)((n + CB - 1) / CB);
   if (nblk <= 3)
-    return launch_cluster<2>(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, (int)n, batch, jitter, info, (cudaStream_t)stream);
-  return launch_cluster<4>(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, (int)n, batch, jitter, info, (cudaStream_t)stream);
+    return launch_cluster<2>(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, (int)n, batch, jitter, info, (int)info_base,
+                             accumulate, (cudaStream_t)stream);
+  return launch_cluster<4>(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, (int)n, batch, jitter, info, (int)info_base,
+                           accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int vargp_chol_inv_cluster(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
+                                      float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
+                                      int32_t* info, void* stream) {
+  return vargp_chol_inv_cluster_ex(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, 0, 0, stream);
 }

@@ -1,7 +1,10 @@
 """Data-parallel ELBO over the GPUs of one box.
 
-Only the minibatch data term shards: rank r gets its own slice of the minibatch and of the likelihood noise;
-Kzz / Cholesky / KL are replicated (identical theta on every rank: same seed, same draw).  Each rank forms
+Only the minibatch data term shards: rank r gets its own slice of the minibatch; Kzz / Cholesky / KL are replicated
+(identical theta on every rank: same seed, same draw).  The drivers here (bench.py, tests) seed every rank identically,
+so the likelihood noise eps_f / eps_u is the SAME tensor on every rank, applied to different data slices: the estimator
+stays unbiased, its noise is correlated across ranks (a per-rank generator for eps_f would decorrelate it; theta must
+stay shared).  Each rank forms
     loss_r = (beta * kl_hypers + kl_u) / R + (N / B_global) * nll_r
 so that the SUM over ranks of the gradients is the full-batch gradient, and one all-reduce(SUM) of a flat
 gradient bucket per step is the only collective (NCCL over NVLink; gloo in the CPU tests)."""

@@ -423,7 +423,8 @@ class CudaOps:
     return bool(self.lib.vargp_chol_cluster_wants(int(n)))
 
   def chol_config(self, block=0, min_n=-1):
-    """Set block size / minimum n of the blocked factorisation; returns (block, min_n) in effect."""
+    """Set block size (0 keeps it, 1 = automatic: 256 with cluster-factored diagonal blocks, else 128) / minimum n of the
+    blocked factorisation; returns (block, min_n) in effect (block 1 while automatic)."""
     r = int(self.lib.vargp_chol_config(int(block), int(min_n)))
     return r & 0xffffffff, r >> 32
 
