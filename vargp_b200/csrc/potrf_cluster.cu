@@ -55,6 +55,22 @@ __device__ __forceinline__ void cl_st_row(float* p, const float (&a)[CB]) {
 // was shared-memory bound.  R = 2 / 1: the block is split over 2 / 4 warps (16 / 8 rows each) when a phase has fewer
 // blocks than warps: a lone warp needs ~1.5 us for a whole block and those phases are on the critical path.
 //   acc[a][b] (+/-)= sum_m At[m][a] * B[m][b]        (At, B already offset to the lane's rows / columns)
+// Blackwell packed fp32 FMA (SASS FFMA2): two IEEE fp32 FMAs per lane and instruction, one operand may be a broadcast
+// scalar with a free negation.  The plain FFMA issues every other cycle per scheduler here, so the block products were
+// FMA-issue bound; the packed form halves the instruction count at identical results (each half is a round-to-nearest fma).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 template <int R> struct mk_vec;
 template <> struct mk_vec<4> { using t = float4; };
 template <> struct mk_vec<2> { using t = float2; };
@@ -72,22 +88,39 @@ template <int R, bool NEG>
 __device__ __forceinline__ void mk_fma(float (&acc)[R][8], const float* __restrict__ At, const float* __restrict__ B) {
   // unrolled by 4 only: the step executes each of these products ONCE per warp, so fully unrolled bodies (24 KB each, four
   // of them plus the diagonal block) were streamed from L2 through the 32 KB instruction cache at every step
+  f32x2 c2[R][4];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c2[i][j] = pk2(acc[i][2 * j], acc[i][2 * j + 1]);
 #pragma unroll 4
   for (int m = 0; m < CB; ++m) {
     float a[R];
     mk_unpack<R>(*reinterpret_cast<const typename mk_vec<R>::t*>(At + m * BLD), a);
     const float4 b0 = *reinterpret_cast<const float4*>(B + m * BLD);
     const float4 b1 = *reinterpret_cast<const float4*>(B + m * BLD + 4);
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const f32x2 b2[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
 #pragma unroll
-    for (int i = 0; i < R; ++i)
+    for (int i = 0; i < R; ++i) {
+      const float ai = NEG ? -a[i] : a[i];
+      const f32x2 a2 = pk2(ai, ai);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(NEG ? -a[i] : a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) c2[i][j] = fma2(a2, b2[j], c2[i][j]);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) upk2(c2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 }
 // same with a ROW-major left operand: acc[a][b] += sum_m A[a][m] * B[m][b]
 template <int R>
 __device__ __forceinline__ void mk_fma_rowA(float (&acc)[R][8], const float* __restrict__ A, const float* __restrict__ B) {
+  f32x2 c2[R][4];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c2[i][j] = pk2(acc[i][2 * j], acc[i][2 * j + 1]);
 #pragma unroll 1
   for (int m4 = 0; m4 < CB; m4 += 4) {
     float4 ar[R];
@@ -98,15 +131,20 @@ __device__ __forceinline__ void mk_fma_rowA(float (&acc)[R][8], const float* __r
       const int m = m4 + u;
       const float4 b0 = *reinterpret_cast<const float4*>(B + m * BLD);
       const float4 b1 = *reinterpret_cast<const float4*>(B + m * BLD + 4);
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const f32x2 b2[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
 #pragma unroll
       for (int i = 0; i < R; ++i) {
         const float a = (u == 0) ? ar[i].x : (u == 1) ? ar[i].y : (u == 2) ? ar[i].z : ar[i].w;
+        const f32x2 a2 = pk2(a, a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a, b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) c2[i][j] = fma2(a2, b2[j], c2[i][j]);
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) upk2(c2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 }
 template <int R>
 __device__ __forceinline__ void mk_zero(float (&acc)[R][8]) {
@@ -165,11 +203,12 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 template <int CS>
 __device__ __forceinline__ void cl_diag_block(float* Lkk, float* Wkk, float* DTloc, float* const (&rDT)[CS], int lane,
                                               int k0, int n, int* s_info, long long* dbgk) {
-  float acc[CB], x[CB];
+  float acc[CB];
+  f32x2 ax[CB];                            // (row `lane` of the block, column `lane` of the inverse), element c
   CL_STAMP(8);
   cl_ld_row(Lkk + lane * BLD, acc);
 #pragma unroll
-  for (int i = 0; i < CB; ++i) x[i] = (i == lane) ? 1.f : 0.f;
+  for (int i = 0; i < CB; ++i) ax[i] = pk2(acc[i], (i == lane) ? 1.f : 0.f);
   float dn = acc[0];                       // next pivot, valid in the lane that owns it
   int bad = 0;
 #pragma unroll
@@ -179,20 +218,26 @@ __device__ __forceinline__ void cl_diag_block(float* Lkk, float* Wkk, float* DTl
     const float inv = __shfl_sync(FULL, r, j);
     const float d = __shfl_sync(FULL, dn, j);
     if (!(d > 0.f) && bad == 0 && k0 + j < n) bad = k0 + j + 1;
-    const float lij = acc[j] * inv;        // lanes >= j; lane j: d * rsqrt(d)
-    acc[j] = lij;
-    const float xj = x[j] * inv;           // D[j][lane]
-    x[j] = xj;
+    float aj, xj;
+    upk2(ax[j], aj, xj);
+    const float lij = aj * inv;            // lanes >= j; lane j: d * rsqrt(d)
+    xj *= inv;                             // D[j][lane]
+    ax[j] = pk2(lij, xj);
     if (j + 1 < CB) {
-      dn = fmaf(-lij, lij, acc[j + 1]);    // lane j+1: its own diagonal after this step, no shuffle on the critical chain
+      float an, xn;
+      upk2(ax[j + 1], an, xn);
+      dn = fmaf(-lij, lij, an);            // lane j+1: its own diagonal after this step, no shuffle on the critical chain
+      const f32x2 m2 = pk2(-lij, -xj);
 #pragma unroll
       for (int c = j + 1; c < CB; ++c) {
         const float lc = __shfl_sync(FULL, lij, c);
-        acc[c] = fmaf(-lij, lc, acc[c]);
-        x[c] = fmaf(-lc, xj, x[c]);
+        ax[c] = fma2(pk2(lc, lc), m2, ax[c]);      // acc[c] -= lij l_cj ;  x[c] -= l_cj D[j][lane]
       }
     }
   }
+  float x[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) upk2(ax[c], acc[c], x[c]);
   CL_STAMP(9);
   if (bad && lane == 0 && *s_info == 0) *s_info = bad;
 #pragma unroll
@@ -293,7 +338,9 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
       if (i0 <= k) i0 += CS;
       const int nrow = (i0 < nblk) ? (nblk - 1 - i0) / CS + 1 : 0;
       const int Ub = nrow + ((rank == owner) ? k + 1 : 0);
-      const int S = (4 * Ub <= kClWarps) ? 4 : ((2 * Ub <= kClWarps) ? 2 : 1);
+      // split factor: a block costs 384 / 640 / 1152 cycles of the shared-memory pipe when 1 / 2 / 4 warps share it and
+      // 2048 / 1024 / 512 cycles of FMA issue per warp: two warps per block while there are at most two blocks, else one
+      const int S = (Ub <= 2) ? 2 : 1;
       float* Wkk = Wst + (rowoff(k) + k) * BLK;
       auto item = [&](auto rtag, int u, int sub) {
         constexpr int R = decltype(rtag)::value;
@@ -365,10 +412,13 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
         mk_fma<R, true>(acc, slots + i * BLK + rr, slots + j * BLK + c0);      // slot i = L_ik^T, pushed here in (B)
         mk_store<R>(T, acc);
       };
+      // the diagonal block of the next step is the critical path: its update runs FIRST and alone (the other warps of
+      // this CTA wait at barrier 14 instead of competing for the shared-memory pipe: 2.0 -> 0.6 us)
+      if (ahead && k >= 0 && (wid & 3) != 0) named_bar(14, kClThreads);
       if (ahead && (wid & 3) == 0) {
         if (k >= 0) {
           trail(std::integral_constant<int, 1>(), k + 1, k + 1, wid >> 2);
-          named_bar(15, 128);
+          named_bar(14, kClThreads);
         }
         if (wid == 0)
           cl_diag_block<CS>(Lst + (rowoff(k + 1) + k + 1) * BLK, Wst + (rowoff(k + 1) + k + 1) * BLK, DT, rDT, lane,
@@ -381,7 +431,7 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
         int Uc = 0;
         for (int i = i0; i < nblk; i += CS) Uc += i + 1;
         if (ahead) Uc -= 1;                           // block (k+1, k+1), the last one of the first row, is warp 0's
-        const int S = (4 * Uc <= nw) ? 4 : ((2 * Uc <= nw) ? 2 : 1);
+        const int S = (Uc <= 3) ? 2 : 1;              // same trade as in (B)
         for (int it = w; it < Uc * S; it += nw) {
           int u = (S == 4) ? it >> 2 : ((S == 2) ? it >> 1 : it);
           const int sub = (S == 4) ? it & 3 : ((S == 2) ? it & 1 : 0);
