@@ -1,10 +1,11 @@
 #!/usr/bin/env bash
-# A/B of environment knobs at the default workload:  scripts/r2_ab.sh <tag> "NAME=ENV1=v,ENV2=v" ...
+# A/B of environment knobs at the default workload (AB_ARGS="--workload permuted_mnist --steps 30 --warmup 5" for another):
+#   scripts/r2_ab.sh <tag> "NAME:ENV1=v,ENV2=v" ...
 set -uo pipefail
 TAG="$1"; shift; OUT=gpurun_out; mkdir -p $OUT
 for spec in "$@"; do
   name="${spec%%:*}"; envs="${spec#*:}"
-  env ${envs//,/ } timeout 120 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-scaled 2> $OUT/${TAG}_ab_$name.err | tail -1 > $OUT/${TAG}_ab_$name.json
+  env ${envs//,/ } timeout 120 python bench.py ${AB_ARGS:---steps 50 --warmup 5} --no-cpu-baseline --no-scaled 2> $OUT/${TAG}_ab_$name.err | tail -1 > $OUT/${TAG}_ab_$name.json
   python - <<PY
 import json
 try:

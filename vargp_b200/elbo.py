@@ -54,8 +54,11 @@ V_SIDE = os.environ.get('VARGP_V_SIDE', '1') != '0'
 # VARGP_WHITEN=0: the per-task-block products through the batched GEMMs even when M fits the shared-memory kernels
 USE_WHITEN = os.environ.get('VARGP_WHITEN', '1') != '0'
 KZZ_LOWER = os.environ.get('VARGP_KZZ_LOWER', '1') != '0'
+SIDE_AFTER_KZZ = os.environ.get('VARGP_SIDE_AFTER_KZZ', 'auto')           # '0' / '1' / 'auto': see marginal_forward
 # SMs the persistent Kzx GEMM may occupy while it runs beside Kzz -> Cholesky (148 - H*C - a margin at the benched shape)
 SIDE_SM_LIMIT = int(os.environ.get('VARGP_SIDE_SM_LIMIT', '112'))
+GZ1_SM_LIMIT = int(os.environ.get('VARGP_GZ1_SM_LIMIT', '64'))           # same for Gz1 beside the adjoint chain (0 = all); measured
+                                                                         # 1168 (no cap) / 1198 (112) / 1207 (74) / 1208 (48) steps/s
 
 
 class _Fork:
@@ -250,7 +253,8 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     if not side_queued:
       side_queued = True
       with fork:
-        ops.scale_rows(x, theta, xs, xn)
+        if not xs_queued:
+          ops.scale_rows(x, theta, xs, xn)
         if STACK_CLASSES:
           # (beside the factorisation chain, whose shared-memory kernels need H*C SMs: the persistent GEMM leaves them free)
           ops.rbf_gram(zs.view(H, 1, C * P, D), zn.view(H, 1, C * P), xs.view(H, 1, B, D), xn.view(H, 1, B), theta,
@@ -258,6 +262,19 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
         else:
           ops.rbf_gram(zs4, zn3, xs.view(H, 1, B, D), xn.view(H, 1, B), theta, Kzx, False, tag='Kzx')
 
+  # SIDE_AFTER_KZZ: the persistent Kzx GEMM must not grab its SMs BEFORE the cluster-cooperative factorisation (120 of 148 SMs,
+  # potrf_cluster.cu) is resident -- its CTAs never yield, and the factorisation would wait for the whole Gram.  The x-side
+  # scaling still starts early; Kzx itself becomes ready together with the factorisation (event after Kzz), is launched after
+  # it, fills the 28 SMs the clusters leave free and takes the rest when they retire.
+  # Measured (B200, Split-MNIST shape, steps/s): t=4 (P=300) 1133 -> 1166, t=1 (P=120) 2496 -> 2543, t=0 (P=60, 2-CTA clusters
+  # on 60 SMs) 3288 -> 3225, Permuted t=9 (blocked factorisation) 245 -> 245: 'auto' = only with 4-CTA clusters.
+  xs_queued = False
+  after_kzz = SIDE_AFTER_KZZ == '1' or (SIDE_AFTER_KZZ == 'auto' and 96 < P <= 320 and hasattr(ops, 'chol_cluster_wants')
+                                        and ops.chol_cluster_wants(P))
+  if KZZ_FIRST and after_kzz and fork.side is not None and shard is None:
+    with fork:
+      ops.scale_rows(x, theta, xs, xn)
+    xs_queued = True
   if not KZZ_FIRST:
     queue_side()
 
@@ -289,6 +306,8 @@ def marginal_forward(theta, Zcat, x, m_all, Lu_all, M, want_kl, ctx=None, shard=
     # the factorisation reads the lower triangle only: a third fewer tiles on the head of the critical chain; the backward
     # pass, which needs the full symmetric Gram, mirrors it on its side branch (marginal_backward)
     ops.rbf_gram(zs4[r], zn3[r], zs4[r], zn3[r], th, Kzz[r], True, tag='Kzz', c_tri='lower' if KZZ_LOWER else None)
+    if xs_queued and not side_queued:
+      fork.mark()                              # Kzx waits for Kzz (see SIDE_AFTER_KZZ above)
     # W = chol(Kzz + eps I)^-1                                                 [gp_utils.py:5-11]
     ops.chol_inv(Kzz[r], L[r], W[r], JITTER, info.view(H, C)[r].reshape(-1) if Hs * Cs == G else
                  info[h0 * C + c0:h0 * C + c1])
@@ -399,7 +418,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
       ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
       if STACK_CLASSES:
-        ops.gemm(Kxbar.view(H, 1, C * P, B), xs.view(H, 1, B, D), Gz1.view(H, 1, C * P, D), tag='Gz1=Wk1*xs')
+        ops.gemm(Kxbar.view(H, 1, C * P, B), xs.view(H, 1, B, D), Gz1.view(H, 1, C * P, D), tag='Gz1=Wk1*xs',
+                 sm_limit=GZ1_SM_LIMIT)
       else:
         ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
       if need_x_grad:
