@@ -57,6 +57,7 @@ KZZ_LOWER = os.environ.get('VARGP_KZZ_LOWER', '1') != '0'
 SIDE_AFTER_KZZ = os.environ.get('VARGP_SIDE_AFTER_KZZ', 'auto')           # '0' / '1' / 'auto': see marginal_forward
 # SMs the persistent Kzx GEMM may occupy while it runs beside Kzz -> Cholesky (148 - H*C - a margin at the benched shape)
 SIDE_SM_LIMIT = int(os.environ.get('VARGP_SIDE_SM_LIMIT', '112'))
+G_PARALLEL = os.environ.get('VARGP_G_PARALLEL', '1') != '0'               # see marginal_backward: 1212 -> 1242 steps/s
 GZ1_SM_LIMIT = int(os.environ.get('VARGP_GZ1_SM_LIMIT', '64'))           # same for Gz1 beside the adjoint chain (0 = all); measured
                                                                          # 1168 (no cap) / 1198 (112) / 1207 (74) / 1208 (48) steps/s
 
@@ -124,6 +125,35 @@ class _Fork:
       ev = torch.cuda.Event()
       ev.record(torch.cuda.current_stream())
       self.side.wait_event(ev)
+
+
+_SIDE2 = {}
+
+
+class _Fork2:
+  """A second helper stream (high priority, like the capture stream of the step): `with par:` queues launches that only
+  depend on what is already queued on the current stream; `par.join()` makes the current stream wait for them."""
+
+  def __init__(self, dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE2:
+      _SIDE2[key] = torch.cuda.Stream(device=dev, priority=-1)
+    self.side = _SIDE2[key]
+    self._ctx = None
+
+  def __enter__(self):
+    self.side.wait_stream(torch.cuda.current_stream())
+    self._ctx = torch.cuda.stream(self.side)
+    self._ctx.__enter__()
+    return self
+
+  def __exit__(self, *exc):
+    self._ctx.__exit__(*exc)
+    self._ctx = None
+    return False
+
+  def join(self):
+    torch.cuda.current_stream().wait_stream(self.side)
 
 
 def _zeros_many(dev, dt, *shapes):
@@ -425,9 +455,20 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
       if need_x_grad:
         ops.gemm(Kxbar.transpose(-1, -2), zs, Gx, tag='Gx=Wk1t*zs')
     # minibatch sums for every pair:  Wbar = tril(Vbar Kzx^T),  G = Nbar = sum_b gv_b V_b V_b^T (lower),  nubar = V gm
+    # Wbar and G are independent lower-triangular products of 180 tiles each (1.2 waves of 148 SMs: the second wave of
+    # each runs on 32 SMs); queued on two streams the tiles of both pack into 2.4 waves (G_PARALLEL, a second helper
+    # stream of the same high priority as the chain)
+    par = _Fork2(dev) if (G_PARALLEL and fork.side is not None and shard is None) else None
+    if par is not None:
+      with par:
+        ops.gemm(Vg, V.transpose(-1, -2), Gm, c_tri='lower', tag='G=Vg*Vt')
+        ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
     ops.gemm(Vbar, Kzx.transpose(-1, -2), Wbar, c_tri='lower', tag='Wbar=Vbar*Kzxt')
-    ops.gemm(Vg, V.transpose(-1, -2), Gm, c_tri='lower', tag='G=Vg*Vt')
-    ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
+    if par is not None:
+      par.join()
+    else:
+      ops.gemm(Vg, V.transpose(-1, -2), Gm, c_tri='lower', tag='G=Vg*Vt')
+      ops.gemm(V, g_mean.unsqueeze(-1), nubar.unsqueeze(-1), tag='nubar=V*gm')
     if shard is not None:        # ... summed over the ranks' minibatch slices, delivered to the owner of each pair
       shard.reduce_scatter(Wbarf, k)
       shard.reduce_scatter(Gf, k)

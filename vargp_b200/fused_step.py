@@ -69,6 +69,17 @@ class FusedElbo:
         p.grad = torch.empty_like(p)
     # ---- draws, in the reference's order ----
     eps_theta = torch.empty(H, D + 1, device=dev, dtype=dt).normal_()
+    # the other two draws depend on nothing: issued here, in the reference's order, on the side stream, so that they run
+    # beside the prologue instead of between the marginal reduction and the likelihood kernel (marginal_forward joins the
+    # side stream before it returns)
+    eps_u = torch.empty((gp.n_v, H, C, gp.n_prev * M), dtype=dt, device=dev) if gp.n_prev else None
+    eps_f = torch.empty(H, F, C, B, device=dev, dtype=dt)
+    with elbo._Fork(dev):
+      if eps_u is not None:
+        # the reference draws u_<t here (vargp.py:138); with ep_var_mean=True nothing depends on it -- the draw is issued
+        # so that the generator stays in step with the reference
+        eps_u.normal_()
+      eps_f.normal_()
     # ---- per-step arena: [terms(3) | pad | info(G) | whiten workspace(1 + G) | nll workspace], one fill ----
     nw, ww = ops.nll_work(H, B), ops.whiten_work(H, C)
     arena = torch.zeros(4 + G + ww + nw, device=dev, dtype=dt)
@@ -83,11 +94,6 @@ class FusedElbo:
     f_mean, f_var, _, _, _ = elbo.marginal_forward(theta, self.Zcat, x, self.m_all, self.Lu_all, M, True, ctx,
                                                    shard=self.shard, zeroed=(info, terms[1], wwork))
     gp._last_info = info
-    if gp.n_prev:
-      # the reference draws u_<t here (vargp.py:138); with ep_var_mean=True nothing depends on it -- the draw is issued
-      # so that the generator stays in step with the reference
-      torch.empty((gp.n_v, H, C, gp.n_prev * M), dtype=dt, device=dev).normal_()
-    eps_f = torch.randn(H, F, C, B, device=dev)
     gmv = torch.empty(2, H, C, B, device=dev, dtype=dt)
     ops.nll_fwd_bwd(f_mean, f_var, eps_f, y, terms[2], gmv[0], gmv[1], work=work, gscale=self.nll_scale)
     # ---- backward ----
