@@ -125,13 +125,6 @@ int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t
 int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                          float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                          int32_t* info, int64_t info_base, int accumulate, void* stream);
-/* Whole-matrix shared-memory variant for n <= 320 (one CTA per matrix, packed 32 x 32 blocks, factorisation and in-place
- * inverse without leaving the SM; potrf_mid.cu): what vargp_chol_inv takes for 128 < n <= 320.  A, L, W must not alias.
- * vargp_chol_mid_config: largest n routed to it (0 disables, < 0 only queries); returns the previous setting. */
-int vargp_chol_inv_mid(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
-                       float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
-                       int32_t* info, void* stream);
-int64_t vargp_chol_mid_config(int64_t max_n);
 /* Cluster-cooperative variant for 32 < n <= 320 (one thread-block cluster of 2 or 4 CTAs per matrix, block rows dealt
  * round-robin to the CTAs' shared memory, panels and rows of the inverse pushed through distributed shared memory, the
  * inverse formed during the factorisation sweep; potrf_cluster.cu): what vargp_chol_inv takes by default at the

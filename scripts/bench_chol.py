@@ -17,11 +17,10 @@ for n in ns:
   L, W = torch.empty_like(A), torch.empty_like(A)
   info = torch.zeros(30, device='cuda', dtype=torch.int32)
   res = {}
-  routes = (('cluster', 0, (33, 320), 0), ('mid', 320, (0, 0), 0), ('blocked_or_small', 0, (0, 0), 0))
+  routes = (('cluster', (33, 320), 0), ('blocked_or_small', (0, 0), 0))
   if n > 320:
-    routes = (('blocked128', 0, (0, 0), 128), ('blocked256_cluster', 0, (33, 320), 256), ('blocked320_cluster', 0, (33, 320), 320))
-  for route, mid, cl, blk in routes:
-    old = ops.chol_mid_config(mid)
+    routes = (('blocked128', (0, 0), 128), ('blocked256_cluster', (33, 320), 256), ('blocked320_cluster', (33, 320), 320))
+  for route, cl, blk in routes:
     old_cl = ops.chol_cluster_config(*cl)
     old_blk = ops.chol_config()
     if blk:
@@ -37,7 +36,6 @@ for n in ns:
     torch.cuda.synchronize()
     res[route] = round(e0.elapsed_time(e1) / 20 * 1e3, 1)
     res[route + '_err'] = float(f'{((L.double().cpu() - L64).norm() / L64.norm()).item():.2e}')
-    ops.chol_mid_config(old)
     ops.chol_cluster_config(*old_cl)
     ops.chol_config(*old_blk)
   print(json.dumps(dict(n=n, batch=30, us=res)), flush=True)

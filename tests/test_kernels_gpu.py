@@ -145,8 +145,6 @@ def test_chol_reports_non_pd(cuda_ops):
 @pytest.mark.parametrize('n,batch,nb', [(600, 4, 128), (1024, 3, 128), (450, 5, 64), (520, 2, 96), (2048, 2, 128),
                                         (300, 6, 0), (129, 3, 128), (1000, 2, 256), (300, 30, 128), (128, 5, 128),
                                         (60, 30, 128), (97, 3, 128), (1, 2, 128), (33, 4, 128), (20, 7, 128),
-                                        (300, 30, 'mid'), (129, 3, 'mid'), (160, 4, 'mid'), (200, 5, 'mid'), (257, 2, 'mid'),
-                                        (320, 3, 'mid'), (180, 33, 'mid'),
                                         (300, 30, 'cluster'), (33, 3, 'cluster'), (60, 30, 'cluster'), (64, 2, 'cluster'),
                                         (65, 2, 'cluster'), (96, 5, 'cluster'), (97, 4, 'cluster'), (120, 30, 'cluster'),
                                         (128, 7, 'cluster'), (129, 3, 'cluster'), (180, 30, 'cluster'), (200, 5, 'cluster'),
@@ -157,7 +155,6 @@ def test_chol_inv_blocked(cuda_ops, n, batch, nb):
   """vargp_chol_inv: GEMM-driven blocked factorisation + inverse (potrf_blocked.cu) incl. ragged block counts;
   nb = 0 is the small-matrix route through the one-CTA kernels."""
   old = cuda_ops.chol_config()
-  old_mid = cuda_ops.chol_mid_config(320 if nb == 'mid' else 0)      # the blocked cases keep the blocked route at n <= 320
   cl = isinstance(nb, str) and nb.startswith('cluster')
   old_cl = cuda_ops.chol_cluster_config(*((33, 320) if cl else (0, 0)))   # potrf_cluster.cu only where asked
   try:
@@ -165,8 +162,6 @@ def test_chol_inv_blocked(cuda_ops, n, batch, nb):
       cuda_ops.chol_config(int(nb[7:]), int(nb[7:]) + 1)
     elif nb == 'cluster':
       assert cuda_ops.chol_cluster_wants(n)
-    elif nb == 'mid':
-      pass
     elif nb:
       cuda_ops.chol_config(nb, nb + 1)
     else:
@@ -196,7 +191,6 @@ def test_chol_inv_blocked(cuda_ops, n, batch, nb):
     assert ((Wd @ Ld - torch.eye(n, dtype=torch.float64)).norm() / n ** 0.5).item() < 2e-4
   finally:
     cuda_ops.chol_config(*old)
-    cuda_ops.chol_mid_config(old_mid)
     cuda_ops.chol_cluster_config(*old_cl)
 
 
@@ -235,27 +229,8 @@ def test_chol_inv_cluster_in_place(cuda_ops):
   close(W, W64, 3e-5, 'inverse')
 
 
-def test_chol_inv_mid_reports_first_bad_pivot(cuda_ops):
-  n = 300
-  A = torch.eye(n, dtype=torch.float64).repeat(3, 1, 1)
-  A[1, 170, 170] = -1.0
-  A[1, 250, 250] = -1.0
-  A[2, 3, 3] = -2.0
-  L, W = torch.empty(3, n, n, device='cuda'), torch.empty(3, n, n, device='cuda')
-  info = torch.zeros(3, device='cuda', dtype=torch.int32)
-  old = cuda_ops.chol_mid_config(320)
-  old_cl = cuda_ops.chol_cluster_config(0, 0)
-  try:
-    cuda_ops.chol_inv(dev(A), L, W, 1e-4, info)
-  finally:
-    cuda_ops.chol_mid_config(old)
-    cuda_ops.chol_cluster_config(*old_cl)
-  assert info.tolist() == [0, 171, 4]
-
-
 def test_chol_inv_blocked_reports_first_bad_pivot(cuda_ops):
   old = cuda_ops.chol_config()
-  old_mid = cuda_ops.chol_mid_config(0)
   old_cl = cuda_ops.chol_cluster_config(0, 0)
   try:
     cuda_ops.chol_config(64, 65)
@@ -270,7 +245,6 @@ def test_chol_inv_blocked_reports_first_bad_pivot(cuda_ops):
     assert info.tolist() == [0, 171, 4]
   finally:
     cuda_ops.chol_config(*old)
-    cuda_ops.chol_mid_config(old_mid)
     cuda_ops.chol_cluster_config(*old_cl)
 
 

@@ -23,9 +23,6 @@
 #include "common.cuh"
 
 extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
-extern "C" int vargp_chol_inv_mid(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
-                                  float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
-                                  int32_t* info, void* stream);
 extern "C" int vargp_chol_inv_small(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                                     float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                                     int32_t* info, int64_t info_base, int accumulate, void* stream);
@@ -82,9 +79,6 @@ static int g_blk_nb = 0;          // diagonal block size of the blocked factoris
                                   // batch 30, us): n=500: 455 -> 320; 1000: 1178 -> 920; 2048: 3642 -> 2785
 static bool g_no_small = false;   // VARGP_CHOL_NO_SMALL=1: diagonal blocks through the chol.cu kernels (A/B timing)
 static int g_blk_min_n = 129;     // matrices at least this large take the blocked path (n <= 128: potrf_small.cu)
-static int g_mid_max_n = 192;     // 128 < n <= this: whole matrix in one CTA's shared memory (potrf_mid.cu); 0 disables.
-                                  // Measured (B200, batch 30, us): n=129: 97 vs 134 blocked; 180: 131 vs 138; 240: 215 vs 172; 300: 354 vs 244
-static int g_mid_min_n = 129;     // VARGP_CHOL_MID_MIN_N: smallest n that takes potrf_mid.cu instead of potrf_small.cu
 
 static int gemm_any(vargp_gemm_t& g, cudaStream_t s) {
   int rc = vargp_gemm_tc(&g, s);
@@ -110,12 +104,6 @@ extern "C" int64_t vargp_chol_config(int64_t block, int64_t min_n) {
   return ((int64_t)g_blk_min_n << 32) | (int64_t)(g_blk_nb ? g_blk_nb : 1);
 }
 
-extern "C" int64_t vargp_chol_mid_config(int64_t max_n) {
-  const int64_t old = g_mid_max_n;
-  if (max_n >= 0) g_mid_max_n = (int)(max_n > 320 ? 320 : max_n);
-  return old;
-}
-
 extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float* L, int64_t l_ld, int64_t l_bs,
                               float* W, int64_t w_ld, int64_t w_bs, int64_t n, int64_t batch, float jitter,
                               int32_t* info, void* stream) {
@@ -132,15 +120,9 @@ extern "C" int vargp_chol_inv(const float* A, int64_t a_ld, int64_t a_bs, float*
     if (e) vargp_chol_config(0, atoll(e));
     e = getenv("VARGP_CHOL_NO_SMALL");
     if (e) g_no_small = atoi(e) != 0;
-    e = getenv("VARGP_CHOL_MID_MAX_N");
-    if (e) vargp_chol_mid_config(atoll(e));
-    e = getenv("VARGP_CHOL_MID_MIN_N");
-    if (e) g_mid_min_n = atoi(e);
   }
   if (vargp_chol_cluster_wants(n))                          // one cluster of 2 / 4 CTAs per matrix (potrf_cluster.cu)
     return vargp_chol_inv_cluster(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
-  if (n >= g_mid_min_n && n <= g_mid_max_n && A != L)      // whole matrix resident in one CTA (potrf_mid.cu)
-    return vargp_chol_inv_mid(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, stream);
   const int nb = g_blk_nb ? g_blk_nb : (vargp_chol_cluster_wants(256) ? 256 : 128);
   if (n <= 128 && !g_no_small)       // whole matrix fits the shared-memory kernel
     return vargp_chol_inv_small(A, a_ld, a_bs, L, l_ld, l_bs, W, w_ld, w_bs, n, batch, jitter, info, 0, 0, stream);

@@ -409,6 +409,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
   """
   ops = _ops()
   H, C, P, B, D, S, M = ctx.dims
+  small = P * B <= (1 << 20)      # Split / Permuted-MNIST sized steps: the side products fit beside the chain (G_PARALLEL, GZ1_SM_LIMIT);
+                                  # at the scaled shape every product fills the chip and the caps cost 5 % (402 vs 383 ms / step)
   G = H * C
   shard = ctx.shard
   k, g0, g1, slots = ctx.part
@@ -449,7 +451,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
       if STACK_CLASSES:
         ops.gemm(Kxbar.view(H, 1, C * P, B), xs.view(H, 1, B, D), Gz1.view(H, 1, C * P, D), tag='Gz1=Wk1*xs',
-                 sm_limit=GZ1_SM_LIMIT)
+                 sm_limit=GZ1_SM_LIMIT if small else 0)
       else:
         ops.gemm(Kxbar, xs.view(H, 1, B, D), Gz1, tag='Gz1=Wk1*xs')
       if need_x_grad:
@@ -458,7 +460,7 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
     # Wbar and G are independent lower-triangular products of 180 tiles each (1.2 waves of 148 SMs: the second wave of
     # each runs on 32 SMs); queued on two streams the tiles of both pack into 2.4 waves (G_PARALLEL, a second helper
     # stream of the same high priority as the chain)
-    par = _Fork2(dev) if (G_PARALLEL and fork.side is not None and shard is None) else None
+    par = _Fork2(dev) if (G_PARALLEL and small and fork.side is not None and shard is None) else None
     if par is not None:
       with par:
         ops.gemm(Vg, V.transpose(-1, -2), Gm, c_tri='lower', tag='G=Vg*Vt')

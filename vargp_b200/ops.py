@@ -66,8 +66,6 @@ def _load():
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
   lib.vargp_chol_inv.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
-  lib.vargp_chol_mid_config.argtypes = [i64]
-  lib.vargp_chol_mid_config.restype = i64
   lib.vargp_chol_config.argtypes = [i64, i64]
   lib.vargp_chol_config.restype = i64
   lib.vargp_chol_cluster_config.argtypes = [i64, i64]
@@ -398,16 +396,6 @@ class CudaOps:
       raise VargpError('chol_inv: shape mismatch')
     self._check(self.lib.vargp_chol_inv(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
                                         info.data_ptr(), self._stream(L)), 'chol_inv')
-
-  def chol_mid_config(self, max_n=-1):
-    """Largest n that vargp_chol_inv routes to the whole-matrix shared-memory kernel (0 disables); returns the previous value."""
-    return int(self.lib.vargp_chol_mid_config(int(max_n)))
-
-  def chol_cluster_config(self, min_n=-1, max_n=-1):
-    """Routing window [min_n, max_n] of the cluster-cooperative kernel (potrf_cluster.cu; 0, 0 disables, negative only
-    queries); returns the previous (min_n, max_n)."""
-    r = int(self.lib.vargp_chol_cluster_config(int(min_n), int(max_n)))
-    return r >> 32, r & 0xffffffff
 
   def chol_inv_cluster(self, K, L, W, jitter, info):
     """The cluster-cooperative kernel directly (32 < n <= 320); K may alias L or W."""
