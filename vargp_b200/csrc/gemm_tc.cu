@@ -447,6 +447,10 @@ bool g_tma_store = true;         // VARGP_TMA_STORE=0: keep the shared-memory tr
 EncodeTiledFn g_encode = nullptr;
 bool g_tc_ready = false;
 
+int tcp_init();                                                                    // gemm_tcp.cu (persistent 1-CTA form)
+bool tcp_wants(const TcParams& p, int64_t ntiles);
+int tcp_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p, int64_t gx,
+               int64_t gy, int64_t nbatch, cudaStream_t stream);
 int tc2_init();                                                                    // gemm_tc2.cu
 int tc2_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream);
 bool tc2_wants(const vargp_gemm_t* g);
@@ -467,6 +471,8 @@ int vargp_tc_init() {
   const char* ts = getenv("VARGP_TMA_STORE");
   if (ts) g_tma_store = atoi(ts) != 0;
   int rc = tc2_init();
+  if (rc) return rc;
+  rc = tcp_init();
   if (rc) return rc;
   g_tc_ready = true;
   return 0;
@@ -525,6 +531,11 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
     if (!p.tma_store) tmC = tmA;
   }
 
+  // more than one wave of tiles: the persistent form (gemm_tcp.cu) overlaps a tile's ramp with the previous tile's store
+  {
+    const int64_t gx = ceil_div(g->N, 128), gy = ceil_div(g->M, TC_BM);
+    if (tcp_wants(p, gx * gy * nbatch)) return tcp_launch(tmA, tmB, tmC, p, gx, gy, nbatch, (cudaStream_t)stream);
+  }
   dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
   launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, tmC, p);
   return launch_status();

@@ -397,6 +397,12 @@ class CudaOps:
     self._check(self.lib.vargp_chol_inv(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
                                         info.data_ptr(), self._stream(L)), 'chol_inv')
 
+  def chol_cluster_config(self, min_n=-1, max_n=-1):
+    """Routing window [min_n, max_n] of the cluster-cooperative kernel (potrf_cluster.cu; 0, 0 disables, negative only
+    queries); returns the previous (min_n, max_n)."""
+    r = int(self.lib.vargp_chol_cluster_config(int(min_n), int(max_n)))
+    return r >> 32, r & 0xffffffff
+
   def chol_inv_cluster(self, K, L, W, jitter, info):
     """The cluster-cooperative kernel directly (32 < n <= 320); K may alias L or W."""
     ap, ald, abs_, n, batch = self._mat_batch(K, 'K')
