@@ -7,7 +7,7 @@ set -uo pipefail
 TAG="${1:-r3p}"; OUT=gpurun_out; mkdir -p $OUT
 NCU="ncu --clock-control none"
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-scaled --no-graph"
-timeout 300 $NCU --metrics gpu__time_duration.sum -s 220 -c 120 --csv --log-file $OUT/${TAG}_launches_split.csv $BENCH > $OUT/${TAG}_launches_split.log 2>&1
+timeout 300 $NCU --metrics gpu__time_duration.sum -s 200 -c 110 --csv --log-file $OUT/${TAG}_launches_split.csv $BENCH > $OUT/${TAG}_launches_split.log 2>&1
 echo "launch list rc $?"; python scripts/ncu_summary.py launches $OUT/${TAG}_launches_split.csv > $OUT/${TAG}_launches_split.txt 2>&1; head -14 $OUT/${TAG}_launches_split.txt
 cap() { name=$1; regex=$2; skip=$3; cnt=$4; shift 4
   timeout 600 $NCU --set full --import-source on -k "regex:$regex" -s $skip -c $cnt -f -o $OUT/${TAG}_$name "$@" > $OUT/${TAG}_$name.log 2>&1
@@ -16,7 +16,7 @@ cap() { name=$1; regex=$2; skip=$3; cnt=$4; shift 4
   ls -la $OUT/${TAG}_$name.ncu-rep | awk '{print $5}'
 }
 cap potrf_cluster_split 'potrf_inv_cluster' 6 2 $BENCH
-cap gemm_tc_split 'gemm_tc_kernel' 72 12 $BENCH
+cap gemm_tc_split 'gemm_tc_kernel|gemm_tcp_kernel' 72 12 $BENCH
 CS=/usr/local/cuda/bin/compute-sanitizer
 K='chol_inv_cluster or (chol_inv_blocked and cluster and (60-30 or 33-3 or 97-4 or 129-3 or 200-5 or 257-2 or 320-3 or 600-4))'
 timeout 900 $CS --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "$K" > $OUT/${TAG}_memcheck_cluster.log 2>&1

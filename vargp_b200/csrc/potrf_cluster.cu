@@ -414,12 +414,11 @@ potrf_inv_cluster_kernel(const float* __restrict__ Ain, int64_t a_ld, int64_t a_
       };
       // the diagonal block of the next step is the critical path: its update runs FIRST and alone (the other warps of
       // this CTA wait at barrier 14 instead of competing for the shared-memory pipe: 2.0 -> 0.6 us)
-      if (ahead && k >= 0 && (wid & 3) != 0) named_bar(14, kClThreads);
+      if (ahead && k >= 0) {
+        if ((wid & 3) == 0) trail(std::integral_constant<int, 1>(), k + 1, k + 1, wid >> 2);
+        named_bar(14, kClThreads);                    // one call site for all 16 warps
+      }
       if (ahead && (wid & 3) == 0) {
-        if (k >= 0) {
-          trail(std::integral_constant<int, 1>(), k + 1, k + 1, wid >> 2);
-          named_bar(14, kClThreads);
-        }
         if (wid == 0)
           cl_diag_block<CS>(Lst + (rowoff(k + 1) + k + 1) * BLK, Wst + (rowoff(k + 1) + k + 1) * BLK, DT, rDT, lane,
                             (k + 1) * CB, n, s_info, dbgk ? dbgk + 16 : nullptr);
