@@ -58,7 +58,9 @@ typedef struct {
   const float* e_theta; /* gamma2 = exp(2 * e_theta[batch offset via e_theta_bs + e_D]) */
   int64_t e_theta_bs[3], e_D;
   /* scheduling hint: a product that runs BESIDE a critical chain (side stream) may be told to occupy at most this many
-   * SMs (0 = all).  Honoured by the persistent 2-CTA kernel, whose CTAs would otherwise own every SM until it is done. */
+   * SMs (0 = all).  Honoured by the persistent 2-CTA kernel, whose CTAs would otherwise own every SM until it is done.
+   * Negative: keep the 1-CTA kernel in its one-tile-per-CTA form (no persistent tile loop), so that launches of a
+   * higher-priority stream can cut in between its waves. */
   int64_t sm_limit;
 } vargp_gemm_t;
 

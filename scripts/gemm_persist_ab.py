@@ -16,11 +16,14 @@ def t(fn, it=30):
 res = {}
 for (name, M, N, K, batch, kw) in (('V=W*Kzx', 300, 512, 300, 30, dict(a_tri='lower', zeroed=True)), ('NV=N*V', 300, 512, 300, 30, {}),
                                    ('G=Vg*Vt', 300, 300, 512, 30, dict(c_tri='lower')), ('Y=Xi*W', 300, 300, 300, 30, dict(b_tri='lower', zeroed=True)),
+                                   ('N=eps*W*Wt', 300, 300, 300, 30, dict(a_tri='lower', b_tri='upper', c_tri='lower', zeroed=True)),
+                                   ('Wbar+=2eps*G*W', 300, 300, 300, 30, dict(b_tri='lower', c_tri='lower', beta=1., zeroed=True)),
                                    ('Gz2', 300, 784, 300, 30, {}), ('one wave', 128, 128, 320, 148, {}), ('two waves', 128, 128, 320, 296, {}),
                                    ('2.43 waves', 128, 128, 320, 360, {})):
   A = torch.randn(batch, M, K, device='cuda'); B = torch.randn(batch, K, N, device='cuda'); C = torch.empty(batch, M, N, device='cuda')
   if kw.get('a_tri') == 'lower': A = A.tril()
   if kw.get('b_tri') == 'lower': B = B.tril()
+  if kw.get('b_tri') == 'upper': B = B.triu()
   res[name] = round(t(lambda: ops.gemm(A, B, C, **kw)), 2)
 print(json.dumps(dict(persist=os.environ.get('VARGP_TC_PERSIST', 'default'), us=res)))
 

@@ -534,8 +534,13 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   // more than one wave of tiles: the persistent form (gemm_tcp.cu) overlaps a tile's ramp with the previous tile's store
   {
     const int64_t gx = ceil_div(g->N, 128), gy = ceil_div(g->M, TC_BM);
-    if (tcp_wants(p, gx * gy * nbatch)) return tcp_launch(tmA, tmB, tmC, p, gx, gy, nbatch, (cudaStream_t)stream);
+    // sm_limit < 0: a product that runs BESIDE a critical chain on a lower-priority stream stays one tile per CTA -- resident
+    // persistent CTAs cannot be preempted, the chain's next launch would wait for the whole product
+    if (g->sm_limit >= 0 && tcp_wants(p, gx * gy * nbatch))
+      return tcp_launch(tmA, tmB, tmC, p, gx, gy, nbatch, (cudaStream_t)stream);
   }
+  // (a 1-D grid in longest-tile-first order was measured here: products alone 15-20 % faster at triangular operands, the step
+  // 2.6 % SLOWER on the same box -- 1242 -> 1210 steps/s, profiles/r3_schedule_ab.txt -- and removed)
   dim3 grid((unsigned)ceil_div(g->N, 128), (unsigned)ceil_div(g->M, TC_BM), (unsigned)nbatch);
   launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, tmC, p);
   return launch_status();

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vargp {
@@ -30,6 +32,17 @@ struct TcParams {
   long long* dbg;                // optional: 8 clock64() stamps of CTA 0's pipeline (vargp_tc_debug; profiling only)
   int32_t sm_limit;              // 2-CTA kernel: at most this many CTAs (0 = one per SM)
   int32_t tma_store;             // 1-CTA kernel: C goes out through cp.async.bulk.tensor stores (tmC valid); 2 = reduce-add (beta == 1)
+};
+
+// Tile order of the 1-CTA kernels.  The tiles of one matrix differ a lot in length when operands are triangular (2 ... 10 slabs
+// at P = 300), and whoever draws two long ones sets the makespan of the launch.  Position q of the launch-wide list =
+// (class q / nbatch of the tiles of a matrix, sorted by DESCENDING slab count on the host, batch q % nbatch): the hardware
+// block scheduler hands positions to SMs as they free up (longest-processing-time-first list scheduling); tiles culled by the
+// output triangle (zero fill only) come last.
+struct TcOrder {
+  uint8_t perm[64];            // sorted position -> tile of the matrix (by * gx + bx); unused when gx * gy > 64
+  int T;                       // gx * gy
+  int nbatch;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -126,6 +139,38 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 extern EncodeTiledFn g_encode;
 extern bool g_tc_ready;
+
+inline TcOrder make_order(const TcParams& p, int64_t gx, int64_t gy, int64_t nbatch, int bm, int bn) {
+  TcOrder od = {};
+  od.T = (int)(gx * gy);
+  od.nbatch = (int)nbatch;
+  if (od.T > 64) return od;
+  static int lpt = -1;                     // VARGP_TC_LPT=0: row-major tile order (A/B)
+  if (lpt < 0) {
+    const char* e = getenv("VARGP_TC_LPT");
+    lpt = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  int nk[64];
+  for (int idx = 0; idx < od.T; ++idx) {
+    const int64_t m0 = (idx / gx) * bm, n0 = (idx % gx) * bn;
+    const bool dead = (p.tri_c == VARGP_TRI_LOWER && n0 > m0 + bm - 1) || (p.tri_c == VARGP_TRI_UPPER && m0 > n0 + bn - 1);
+    int64_t k_lo = 0, k_hi = p.K;
+    if (p.tri_a == VARGP_TRI_LOWER) k_hi = k_hi < m0 + bm ? k_hi : m0 + bm;
+    if (p.tri_a == VARGP_TRI_UPPER) k_lo = k_lo > m0 ? k_lo : m0;
+    if (p.tri_b == VARGP_TRI_LOWER) k_lo = k_lo > n0 ? k_lo : n0;
+    if (p.tri_b == VARGP_TRI_UPPER) k_hi = k_hi < n0 + bn ? k_hi : n0 + bn;
+    nk[idx] = (dead || k_hi <= k_lo) ? 0 : (int)((k_hi + TC_BK - 1) / TC_BK - k_lo / TC_BK);
+    od.perm[idx] = (uint8_t)idx;
+  }
+  if (!lpt) return od;
+  for (int a = 1; a < od.T; ++a) {         // insertion sort, descending, stable
+    const uint8_t v = od.perm[a];
+    int b = a;
+    while (b > 0 && nk[od.perm[b - 1]] < nk[v]) { od.perm[b] = od.perm[b - 1]; --b; }
+    od.perm[b] = v;
+  }
+  return od;
+}
 
 // operand (rows x K) described by (row stride rs, k stride cs): build a 5-D map (inner, outer, b2, b1, b0)
 // box_rows: operand rows per TMA box of a K-contiguous operand (an M/N-contiguous one is fetched in 32-row chunks)

@@ -447,7 +447,8 @@ def marginal_backward(ctx, g_mean, g_var, g_kl, need_x_grad=False, last_raw=Fals
         for (h0, h1, c0, c1) in rects:
           ops.sym_phi(Kzz[h0:h1, c0:c1], mirror=True)
         kzz_ready, ctx.kzz_lower = fork.side_event(), False
-      ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True)
+      ops.gemm(W.transpose(-1, -2), Vbar, Kxbar, a_tri='upper', tag='Kxbar=Wt*Vbar', zeroed=True,
+               sm_limit=-1 if small else 0)     # beside the chain: one tile per CTA, so that the chain's launches can cut in
       ops.rbf_bwd_prep(Kxbar, Kzx, r1, csum)                    # Kxbar <- Kxbar * Kzx ; col sums over (c, i)
       if STACK_CLASSES:
         ops.gemm(Kxbar.view(H, 1, C * P, B), xs.view(H, 1, B, D), Gz1.view(H, 1, C * P, D), tag='Gz1=Wk1*xs',
