@@ -283,6 +283,12 @@ int vargp_yogi_step(float* p, const float* g, float* m, float* v, int64_t n, flo
 int64_t vargp_peer_buffer_floats(int64_t n);
 int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int rank, int64_t n, float* flat_g, float* p, float* m,
                               float* v, float lr, float b1, float b2, float eps, float* pows, uint32_t* ctr, void* stream);
+/* Same with the in-switch reduction (NVLS): `multicast` is the multicast mapping of the ranks' symmetric buffers
+ * (torch.distributed._symmetric_memory: handle.multicast_ptr); the reduce kernel then issues ONE
+ * multimem.ld_reduce per 16 bytes instead of a load from every peer.  NULL = the peer-load form above. */
+int vargp_peer_allreduce_yogi_nvls(float* const* peer_bufs, const float* multicast, int world, int rank, int64_t n,
+                                   float* flat_g, float* p, float* m, float* v, float lr, float b1, float b2, float eps,
+                                   float* pows, uint32_t* ctr, void* stream);
 
 #ifdef __cplusplus
 }

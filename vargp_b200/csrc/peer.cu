@@ -39,6 +39,14 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {          // peer me
   return v;
 }
 
+// in-switch reduction over the multicast mapping of the symmetric buffer (NVLS): the sum of every rank's 16 bytes
+__device__ __forceinline__ float4 ld_reduce4(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // ctr[0] = steps completed so far, ctr[1] / ctr[2] = ticket counters of the two kernels (zero between launches)
 __global__ void __launch_bounds__(256)
 peer_stage_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t npad, const float* __restrict__ g, unsigned* ctr) {
@@ -64,7 +72,7 @@ peer_stage_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t npad, co
 }
 
 __global__ void __launch_bounds__(256)
-peer_reduce_yogi_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t npad, float* __restrict__ gsum,
+peer_reduce_yogi_kernel(PeerBufs pb, const float* mc, int world, int rank, int64_t n4, int64_t npad, float* __restrict__ gsum,
                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
                         float eps, float* pows, unsigned* ctr) {
   pdl_enter();
@@ -92,9 +100,13 @@ peer_reduce_yogi_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t np
 #pragma unroll
     for (int q = 0; q < kPU; ++q) {
       const int64_t i = i0 + q * stride;
+      if (mc) {                     // NVLS: ONE load, the NVSwitch sums the ranks' staging buffers (multicast address)
+        if (i < n4) t[q][0] = ld_reduce4(mc + off + 4 * i);
+      } else {
 #pragma unroll
-      for (int r = 0; r < kPeerMax; ++r)
-        if (r < world && i < n4) t[q][r] = ld_peer4(pb.buf[r] + off + 4 * i);
+        for (int r = 0; r < kPeerMax; ++r)
+          if (r < world && i < n4) t[q][r] = ld_peer4(pb.buf[r] + off + 4 * i);
+      }
       if (i < n4) { pp[q] = p4[i]; mm[q] = m4[i]; vv[q] = v4[i]; }
     }
 #pragma unroll
@@ -102,9 +114,13 @@ peer_reduce_yogi_kernel(PeerBufs pb, int world, int rank, int64_t n4, int64_t np
       const int64_t i = i0 + q * stride;
       if (i >= n4) break;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mc) {
+        s = t[q][0];
+      } else {
 #pragma unroll
-      for (int r = 0; r < kPeerMax; ++r)
-        if (r < world) { s.x += t[q][r].x; s.y += t[q][r].y; s.z += t[q][r].z; s.w += t[q][r].w; }
+        for (int r = 0; r < kPeerMax; ++r)
+          if (r < world) { s.x += t[q][r].x; s.y += t[q][r].y; s.z += t[q][r].z; s.w += t[q][r].w; }
+      }
       g4[i] = s;
       const float gs[4] = {s.x, s.y, s.z, s.w};
       float* pe[4] = {&pp[q].x, &pp[q].y, &pp[q].z, &pp[q].w};
@@ -149,9 +165,9 @@ using namespace vargp;
 // halves, 32 flag words); the buffer must be zero-filled once before the first step
 extern "C" int64_t vargp_peer_buffer_floats(int64_t n) { return 2 * ((n + 3) / 4 * 4) + 32; }
 
-extern "C" int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int rank, int64_t n, float* flat_g, float* p,
-                                         float* m, float* v, float lr, float b1, float b2, float eps, float* pows,
-                                         uint32_t* ctr, void* stream) {
+extern "C" int vargp_peer_allreduce_yogi_nvls(float* const* peer_bufs, const float* multicast, int world, int rank, int64_t n,
+                                              float* flat_g, float* p, float* m, float* v, float lr, float b1, float b2,
+                                              float eps, float* pows, uint32_t* ctr, void* stream) {
   if (!peer_bufs || world < 1 || world > kPeerMax || rank < 0 || rank >= world || n < 1 || !flat_g || !p || !m || !v || !pows || !ctr)
     return VARGP_ERR_ARG;
   if (n % 4 != 0) return VARGP_ERR_UNSUPPORTED;        // the caller pads the flat buffers to a multiple of 4 elements
@@ -171,7 +187,14 @@ extern "C" int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int
            reinterpret_cast<unsigned*>(ctr));
   int rc = launch_status();
   if (rc) return rc;
-  launch_k(peer_reduce_yogi_kernel, dim3((unsigned)blocks), dim3(256), 0, s, pb, world, rank, n4, npad, flat_g, p, m, v, lr, b1, b2,
-           eps, pows, reinterpret_cast<unsigned*>(ctr));
+  if (multicast && reinterpret_cast<uintptr_t>(multicast) % 16 != 0) return VARGP_ERR_ARG;
+  launch_k(peer_reduce_yogi_kernel, dim3((unsigned)blocks), dim3(256), 0, s, pb, multicast, world, rank, n4, npad, flat_g, p, m, v,
+           lr, b1, b2, eps, pows, reinterpret_cast<unsigned*>(ctr));
   return launch_status();
+}
+
+extern "C" int vargp_peer_allreduce_yogi(float* const* peer_bufs, int world, int rank, int64_t n, float* flat_g, float* p,
+                                         float* m, float* v, float lr, float b1, float b2, float eps, float* pows,
+                                         uint32_t* ctr, void* stream) {
+  return vargp_peer_allreduce_yogi_nvls(peer_bufs, nullptr, world, rank, n, flat_g, p, m, v, lr, b1, b2, eps, pows, ctr, stream);
 }

@@ -99,6 +99,7 @@ def _load():
   lib.vargp_peer_buffer_floats.argtypes = [i64]
   lib.vargp_peer_buffer_floats.restype = i64
   lib.vargp_peer_allreduce_yogi.argtypes = [vp, ctypes.c_int, ctypes.c_int, i64, vp, vp, vp, vp] + [ctypes.c_float] * 4 + [vp, vp, vp]
+  lib.vargp_peer_allreduce_yogi_nvls.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, i64, vp, vp, vp, vp] + [ctypes.c_float] * 4 + [vp, vp, vp]
   lib.vargp_hyper_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
   lib.vargp_hyper_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
   return lib
@@ -582,9 +583,18 @@ class CudaOps:
   def peer_buffer_floats(self, n):
     return int(self.lib.vargp_peer_buffer_floats(n))
 
-  def peer_allreduce_yogi(self, peer_ptrs, rank, flat_g, p, m, v, lr, b1, b2, eps, pows, ctr):
-    """flat_g <- sum over ranks (through the ranks' symmetric-memory staging buffers `peer_ptrs`), then the Yogi update."""
+  def peer_allreduce_yogi(self, peer_ptrs, rank, flat_g, p, m, v, lr, b1, b2, eps, pows, ctr, multicast=0):
+    """flat_g <- sum over ranks (through the ranks' symmetric-memory staging buffers `peer_ptrs`; with `multicast`, the
+    multicast mapping of those buffers, by in-switch reduction), then the Yogi update."""
     arr = (vp * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+    if multicast:
+      if ctr.dtype != torch.int32 or ctr.numel() < 4:
+        raise VargpError('peer_allreduce_yogi: ctr must be an int32 tensor of 4 words')
+      self._check(self.lib.vargp_peer_allreduce_yogi_nvls(arr, int(multicast), len(peer_ptrs), int(rank), p.numel(),
+                                                          _f32(flat_g, 'flat_g'), _f32(p, 'p'), _f32(m, 'm'), _f32(v, 'v'),
+                                                          float(lr), float(b1), float(b2), float(eps), _f32(pows, 'pows'),
+                                                          ctr.data_ptr(), self._stream(p)), 'peer_allreduce_yogi_nvls')
+      return
     if ctr.dtype != torch.int32 or ctr.numel() < 4:
       raise VargpError('peer_allreduce_yogi: ctr must be an int32 tensor of 4 words')
     self._check(self.lib.vargp_peer_allreduce_yogi(arr, len(peer_ptrs), int(rank), p.numel(), _f32(flat_g, 'flat_g'), _f32(p, 'p'),

@@ -113,7 +113,20 @@ class FlatYogi:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     if not int(flag.item()):
       return False
-    self.peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, rank=dist.get_rank(group),
+    # NVLS: with a multicast mapping of the symmetric buffers the reduce kernel lets the NVSwitch add the ranks' gradients
+    # (one multimem.ld_reduce per 16 bytes instead of a load from every peer); VARGP_PEER_NVLS=0 keeps the peer loads
+    import os
+    mc = 0
+    if os.environ.get('VARGP_PEER_NVLS', '1') != '0':
+      try:
+        mc = int(hdl.multicast_ptr or 0)
+      except Exception:
+        mc = 0
+    mflag = torch.tensor([1 if mc else 0], device=self.flat_g.device)
+    dist.all_reduce(mflag, op=dist.ReduceOp.MIN, group=group)
+    if not int(mflag.item()):
+      mc = 0
+    self.peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, rank=dist.get_rank(group), multicast=mc,
                      ctr=torch.zeros(4, dtype=torch.int32, device=self.flat_g.device))
     return True
 
@@ -122,4 +135,5 @@ class FlatYogi:
     """flat_g <- sum over ranks; Yogi update with the summed gradient (fused, peer memory)."""
     pr = self.peer
     self._ops().peer_allreduce_yogi(pr['ptrs'], pr['rank'], self.flat_g, self.flat_p, self.m, self.v, self.lr,
-                                    self.betas[0], self.betas[1], self.eps, self.pows, pr['ctr'])
+                                    self.betas[0], self.betas[1], self.eps, self.pows, pr['ctr'],
+                                    multicast=pr.get('multicast', 0))
