@@ -80,6 +80,11 @@ int vargp_gemm(const vargp_gemm_t* g, void* stream);
 /* tcgen05 / TMA path (3xTF32): same contract as vargp_gemm restricted to K-contiguous operands
  * (a_cs == 1, b_rs == 1), 16-byte aligned rows; returns -2 if the problem does not qualify. */
 int vargp_gemm_tc(const vargp_gemm_t* g, void* stream);
+/* Launches of the 1-CTA kernel whose C goes out through the TMA engine may take its PERSISTENT form (one CTA per SM working
+ * through the tiles handed out by a launch-wide counter, longest tiles first; gemm_tcp.cu).  mode: 0 off, 1 launches of
+ * more than one wave of tiles (default), 2 every such launch, 3 from four waves; negative only queries.  Returns the
+ * previous mode.  A descriptor with sm_limit < 0 always keeps the one-tile-per-CTA form. */
+int64_t vargp_tc_persist_config(int64_t mode);
 /* vargp_gemm_tc hands problems with at least `min_tiles` 256 x 256 output tiles to the persistent 2-CTA
  * (cta_group::2) kernel; < 0 disables it, INT64_MIN only queries.  Returns the previous setting.
  * vargp_tc2_launch_count: launches of that kernel since load. */

@@ -122,6 +122,78 @@ def test_tc_rbf_epilogue(cuda_ops, H, C, P, B, D):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# persistent form of the 1-CTA kernel (gemm_tcp.cu): forced for every TMA-store launch through vargp_tc_persist_config(2)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def force_persist(cuda_ops):
+  old = cuda_ops.tc_persist_config(2)
+  yield cuda_ops
+  cuda_ops.tc_persist_config(old)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 96), (132, 68, 44), (300, 512, 300), (300, 784, 300), (1000, 1000, 320)])
+@pytest.mark.parametrize('ta,tb', [(False, True), (False, False), (True, False), (True, True)])
+def test_tcp_gemm_majors(force_persist, M, N, K, ta, tb):
+  ops = force_persist
+  A, B, Ad, Bd = make((7,), M, N, K, ta, tb)
+  Cd = torch.full((7, M, N), float('nan'), device='cuda')
+  n0 = ops.tc_calls
+  ops.gemm(Ad, Bd, Cd)
+  assert ops.tc_calls == n0 + 1
+  assert relerr(Cd, A @ B) < 1e-6, (M, N, K, ta, tb)
+
+
+@pytest.mark.parametrize('kw', [
+  dict(a_tri='lower'), dict(a_tri='upper', ta=True), dict(b_tri='lower'), dict(a_tri='lower', b_tri='upper', tb=True, c_tri='lower'),
+  dict(c_tri='lower', beta=1.0, tb=True), dict(c_tri='upper', alpha=-0.5)])
+def test_tcp_gemm_flags_match_the_one_tile_form_bitwise(cuda_ops, kw):
+  """Triangular operands give tiles of 2 ... 10 slabs (and culled ones): the work-stealing tile loop in longest-first order
+  must produce exactly what one tile per CTA produces -- the same instruction sequence per partial sum."""
+  kw = dict(kw)
+  ta, tb = kw.pop('ta', False), kw.pop('tb', False)
+  n = 300
+  A, B, Ad, Bd = make((5, 6), n, n, n, ta, tb)
+  for t64, td, tri in ((A, Ad, kw.get('a_tri')), (B, Bd, kw.get('b_tri'))):
+    if tri:
+      mask = torch.ones(n, n).tril(-1).bool() if tri == 'upper' else torch.ones(n, n).triu(1).bool()
+      t64.masked_fill_(mask, 0.0)
+      td.masked_fill_(mask.cuda(), 0.0)
+  C0 = rnd(5, 6, n, n, seed=3)
+  C64 = C0.clone()
+  EMU.gemm(A, B, C64, **kw)
+  outs = []
+  for mode in (0, 2):
+    old = cuda_ops.tc_persist_config(mode)
+    try:
+      Cd = C0.to('cuda', torch.float32)
+      cuda_ops.gemm(Ad, Bd, Cd, zeroed=True, **kw)
+      outs.append(Cd)
+    finally:
+      cuda_ops.tc_persist_config(old)
+  assert relerr(outs[1], C64) < 1e-6, kw
+  if kw.get('beta', 0.0) == 0.0:          # beta = 1 goes through cp.reduce adds at L2: same values, no ordering guarantee needed
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_tcp_rbf_epilogue(force_persist):
+  """Fused gamma^2 exp(.) epilogue (and the symmetric lower-triangular Kzz form with culled tiles) in the persistent loop."""
+  ops = force_persist
+  H, C, P, B, D = 3, 10, 300, 512, 784
+  theta = 0.1 * rnd(H, D + 1, seed=1) + math.log(math.sqrt(D) / 3)
+  zs, xs = torch.rand(H, C, P, D, dtype=torch.float64) / 8, torch.rand(H, 1, B, D, dtype=torch.float64) / 8
+  zn, xn = (zs * zs).sum(-1), (xs * xs).sum(-1)
+  K64, Kzz64 = torch.empty(H, C, P, B, dtype=torch.float64), torch.empty(H, C, P, P, dtype=torch.float64)
+  EMU.rbf_gram(zs, zn, xs, xn, theta, K64, False)
+  EMU.rbf_gram(zs, zn, zs, zn, theta, Kzz64, True)
+  f = lambda t: t.to('cuda', torch.float32)
+  Kd, Kzzd = torch.empty(H, C, P, B, device='cuda'), torch.full((H, C, P, P), float('nan'), device='cuda')
+  ops.rbf_gram(f(zs), f(zn), f(xs), f(xn), f(theta), Kd, False)
+  ops.rbf_gram(f(zs), f(zn), f(zs), f(zn), f(theta), Kzzd, True, c_tri='lower')
+  assert relerr(Kd, K64) < 1e-6 and relerr(Kzzd, Kzz64.tril()) < 1e-6
+  assert torch.equal(Kzzd.triu(1), torch.zeros_like(Kzzd))
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # persistent 2-CTA kernel (gemm_tc2.cu): forced for every qualifying shape through vargp_tc2_config(1)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.fixture

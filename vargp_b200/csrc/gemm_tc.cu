@@ -449,6 +449,7 @@ bool g_tc_ready = false;
 
 int tcp_init();                                                                    // gemm_tcp.cu (persistent 1-CTA form)
 bool tcp_wants(const TcParams& p, int64_t ntiles);
+int tcp_config(int mode);
 int tcp_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p, int64_t gx,
                int64_t gy, int64_t nbatch, cudaStream_t stream);
 int tc2_init();                                                                    // gemm_tc2.cu
@@ -545,6 +546,11 @@ extern "C" int vargp_gemm_tc(const vargp_gemm_t* g, void* stream) {
   launch_k(gemm_tc_kernel<128, 3, 1>, dim3(grid), dim3(TC_THREADS), TcCfg<128, 3>::SMEM_BYTES, (cudaStream_t)stream, tmA, tmB, tmC, p);
   return launch_status();
 }
+
+/* routing of the persistent form of the 1-CTA kernel (gemm_tcp.cu): 0 off, 1 launches of more than one wave of tiles
+ * (default; VARGP_TC_PERSIST), 2 every TMA-store launch, 3 launches of at least four waves; < 0 only queries.
+ * Returns the previous mode. */
+extern "C" int64_t vargp_tc_persist_config(int64_t mode) { return tcp_config((int)mode); }
 
 /* profiling aid: device buffer of >= 8 int64 that CTA (0,0,0) of every following vargp_gemm_tc launch (1-CTA kernel)
  * fills with clock64() stamps: entry, setup done, first slab landed, first slab issued, first partial sum ready,

@@ -413,6 +413,12 @@ int tcp_init() {
   return 0;
 }
 
+int tcp_config(int mode) {
+  const int old = g_tp_mode;
+  if (mode >= 0 && mode <= 3) g_tp_mode = mode;
+  return old;
+}
+
 bool tcp_wants(const TcParams& p, int64_t ntiles) {
   if (!p.tma_store || g_tp_mode == 0 || g_tp_sms <= 0) return false;
   // Resident persistent CTAs cannot be preempted and assume that all of them ARE resident: beside the capped side-branch

@@ -62,6 +62,8 @@ def _load():
   lib.vargp_tc2_config.argtypes = [i64]
   lib.vargp_tc2_config.restype = i64
   lib.vargp_tc2_launch_count.restype = i64
+  lib.vargp_tc_persist_config.argtypes = [i64]
+  lib.vargp_tc_persist_config.restype = i64
   lib.vargp_scale_rows.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, vp, vp]
   lib.vargp_chol.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, ctypes.c_float, vp, vp]
   lib.vargp_trtri.argtypes = [vp, i64, i64, vp, i64, i64, i64, i64, vp]
@@ -397,6 +399,11 @@ class CudaOps:
       raise VargpError('chol_inv: shape mismatch')
     self._check(self.lib.vargp_chol_inv(ap, ald, abs_, lp, lld, lbs, wp, wld, wbs, n, batch, float(jitter),
                                         info.data_ptr(), self._stream(L)), 'chol_inv')
+
+  def tc_persist_config(self, mode=-1):
+    """Routing of the persistent form of the 1-CTA tensor-core GEMM (gemm_tcp.cu): 0 off, 1 above one wave of tiles (default),
+    2 always, 3 from four waves; negative only queries.  Returns the previous mode."""
+    return int(self.lib.vargp_tc_persist_config(int(mode)))
 
   def chol_cluster_config(self, min_n=-1, max_n=-1):
     """Routing window [min_n, max_n] of the cluster-cooperative kernel (potrf_cluster.cu; 0, 0 disables, negative only
