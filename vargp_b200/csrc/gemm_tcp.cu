@@ -7,8 +7,10 @@
 //   * barriers, TMEM and tensor-map prefetch are set up once per CTA,
 //   * the TMA producer and the splitter run ahead into the NEXT tile's slabs while the epilogue warps store the current one
 //     (the store staging boxes are their own 32 KB, not the operand ring, which is never idle here),
-//   * the cross-term accumulator is double-buffered across tiles (TMEM: main0 | main1 | lo0 | lo1 = 512 columns), so the
-//     MMA issuer starts the next tile without waiting for the epilogue's last drain.
+//   * the hi*hi partial sums have THREE TMEM buffers instead of two (main0 | main1 | main2 | lo = 512 columns): the epilogue
+//     warps drain a tile's cross-term accumulator right after its last MMA and only then store, so the MMA issuer waits
+//     ~0.7 us for `lo` and then has three slabs of the next tile to run under the ~2.5 us store (two buffers + a
+//     double-buffered `lo` left it idle for ~1.9 us per tile).
 // Same contract, numerics and per-slab promotion scheme as gemm_tc_kernel (every partial sum is produced by the same
 // instruction sequence: results are bit-identical); only launches with p.tma_store != 0 come here.
 #include "tc_common.cuh"
@@ -24,6 +26,7 @@ constexpr int TP_BOXES = TP_EPI_WARPS * 4096;                    // one 32 x 32 
 constexpr int TP_SMEM_BYTES = TP_RING + TP_BOXES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TP_EC = TP_BN / 2;                                 // output columns per epilogue warp
 constexpr int TP_NQ = 4;                                         // depth of the per-CTA tile queue
+constexpr int TP_NACC = 3;                                       // hi*hi partial-sum buffers in TMEM (main0 | main1 | main2 | lo)
 
 struct TpTile {
   int64_t m0, n0;
@@ -93,10 +96,10 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* full_bar = bars;                       // TMA landed
   uint64_t* conv_bar = bars + TP_STAGES;           // hi/lo split done
   uint64_t* empty_bar = bars + 2 * TP_STAGES;      // MMAs that read the stage retired
-  uint64_t* accf_bar = bars + 3 * TP_STAGES;       // [2] hi*hi partial sum of a slab complete
-  uint64_t* acce_bar = bars + 3 * TP_STAGES + 2;   // [2] partial-sum buffer drained by the epilogue
-  uint64_t* lof_bar = bars + 3 * TP_STAGES + 4;    // [2] cross-term accumulator of a tile complete
-  uint64_t* loe_bar = bars + 3 * TP_STAGES + 6;    // [2] ... drained by the epilogue
+  uint64_t* accf_bar = bars + 3 * TP_STAGES;       // [TP_NACC] hi*hi partial sum of a slab complete
+  uint64_t* acce_bar = bars + 3 * TP_STAGES + 3;   // [TP_NACC] partial-sum buffer drained by the epilogue
+  uint64_t* lof_bar = bars + 3 * TP_STAGES + 6;    // cross-term accumulator of a tile complete
+  uint64_t* loe_bar = bars + 3 * TP_STAGES + 7;    // ... drained by the epilogue
   uint64_t* tqf_bar = bars + 3 * TP_STAGES + 8;    // [TP_NQ] tile queue entry published by the producer thread
   uint64_t* tqe_bar = bars + 3 * TP_STAGES + 8 + TP_NQ;   // [TP_NQ] ... read by the 13 consumer warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TP_STAGES + 8 + 2 * TP_NQ);
@@ -119,12 +122,12 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_init(&conv_bar[s], 4);
         mbar_init(&empty_bar[s], 1);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < TP_NACC; ++b) {
         mbar_init(&accf_bar[b], 1);
         mbar_init(&acce_bar[b], TP_EPI_WARPS);
-        mbar_init(&lof_bar[b], 1);
-        mbar_init(&loe_bar[b], TP_EPI_WARPS);
       }
+      mbar_init(lof_bar, 1);
+      mbar_init(loe_bar, TP_EPI_WARPS);
       for (int i = 0; i < TP_NQ; ++i) {
         mbar_init(&tqf_bar[i], 1);
         mbar_init(&tqe_bar[i], 1 + 4 + TP_EPI_WARPS);
@@ -201,19 +204,19 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (q < 0) break;
       const TpTile ti = tp_tile(p, od, q, gx);
       if (ti.nk == 0) continue;
-      const int lob = lt & 1;
-      mbar_wait(&loe_bar[lob], ((lt >> 1) & 1) ^ 1);       // the tile before last has handed this cross-term buffer back
+      mbar_wait(loe_bar, (lt & 1) ^ 1);                     // the previous tile's cross terms have been drained (right after its
+                                                            // last MMA, BEFORE its store: the store overlaps three slabs here)
       for (int it = 0; it < ti.nk; ++it, ++g) {
         const int s = g % TP_STAGES;
         const uint32_t ph = (g / TP_STAGES) & 1;
-        const int buf = g & 1;
+        const int buf = g % TP_NACC;
         mbar_wait(&conv_bar[s], ph);
-        mbar_wait(&acce_bar[buf], ((g >> 1) & 1) ^ 1);      // epilogue has drained this partial-sum buffer
+        mbar_wait(&acce_bar[buf], ((g / TP_NACC) & 1) ^ 1); // epilogue has drained this partial-sum buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t a_hi = smem_u32(sA_hi + s * TC_TILE_BYTES), a_lo = smem_u32(sA_lo + s * TC_TILE_BYTES);
           const uint32_t b_hi = smem_u32(sB_hi + s * TP_B_TILE), b_lo = smem_u32(sB_lo + s * TP_B_TILE);
-          const uint32_t t_main = tmem_base + (uint32_t)(buf * TP_BN), t_lo = tmem_base + (uint32_t)((2 + lob) * TP_BN);
+          const uint32_t t_main = tmem_base + (uint32_t)(buf * TP_BN), t_lo = tmem_base + (uint32_t)(TP_NACC * TP_BN);
 #pragma unroll
           for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
             const uint32_t oa = p.a_mn ? k8 * 1024 : k8 * 32;
@@ -229,7 +232,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           umma_commit(&empty_bar[s]);
           umma_commit(&accf_bar[buf]);
-          if (it == ti.nk - 1) umma_commit(&lof_bar[lob]);
+          if (it == ti.nk - 1) umma_commit(lof_bar);
           if (g == 0) TP_STAMP(3);
         }
         __syncwarp();
@@ -316,8 +319,8 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       };
       if (ti.nk > 0) {
         for (int it = 0; it < ti.nk; ++it, ++g) {
-          const int buf = g & 1;
-          mbar_wait(&accf_bar[buf], (g >> 1) & 1);
+          const int buf = g % TP_NACC;
+          mbar_wait(&accf_bar[buf], (g / TP_NACC) & 1);
           if (g == 0 && warp == 6 && lane == 0) TP_STAMP(4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           drain(t_row + (uint32_t)(buf * TP_BN));
@@ -325,13 +328,12 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(&acce_bar[buf]);
         }
-        const int lob = lt & 1;
-        mbar_wait(&lof_bar[lob], (lt >> 1) & 1);
+        mbar_wait(lof_bar, lt & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        drain(t_row + (uint32_t)((2 + lob) * TP_BN));
+        drain(t_row + (uint32_t)(TP_NACC * TP_BN));
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&loe_bar[lob]);
+        if (lane == 0) mbar_arrive(loe_bar);
         if (lt == 0 && warp == 6 && lane == 0) TP_STAMP(5);
         ++lt;
       }
