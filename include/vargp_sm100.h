@@ -9,7 +9,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to fp32 unless stated otherwise; sizes and strides are int64, in
  *     ELEMENTS; `stream` is a cudaStream_t passed as void*.
- *   - the library never allocates, frees or retains memory; all work is asynchronous on `stream`.
+ *   - the library never allocates, frees or retains CALLER memory (its one own device allocation is an 8 KB pool of tile
+ *     counters for the persistent GEMM, made by vargp_init); all work is asynchronous on `stream`.
  *   - return value: 0 ok, <0 invalid argument (see vargp_strerror), >0 a cudaError_t.
  *   - H = hyper samples, C = classes (output GPs), P = inducing points per class over all tasks,
  *     M = inducing points per task, S = P / M tasks, B = minibatch, D = input dims, F = likelihood samples.
