@@ -391,6 +391,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+extern int g_device;             // api.cu: the device of vargp_init
 static int g_tp_sms = 0;
 static unsigned* g_tp_ctr = nullptr;   // pool of (next position, CTAs done) pairs, one per launch in flight; self re-arming
 static unsigned g_tp_seq = 0;
@@ -400,14 +401,17 @@ int g_tp_mode = 1;               // VARGP_TC_PERSIST: 0 off, 1 on for launches o
 int tcp_init() {
   cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  int dev = 0;
-  cudaGetDevice(&dev);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int dev = g_device >= 0 ? g_device : cur;         // the device vargp_init was given, whatever is current
   e = cudaDeviceGetAttribute(&g_tp_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess || g_tp_sms <= 0) return e != cudaSuccess ? (int)e : VARGP_ERR_NOT_INIT;
   if (!g_tp_ctr) {
+    if (dev != cur) cudaSetDevice(dev);
     e = cudaMalloc(&g_tp_ctr, TP_CTR_SLOTS * 2 * sizeof(unsigned));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemset(g_tp_ctr, 0, TP_CTR_SLOTS * 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(g_tp_ctr, 0, TP_CTR_SLOTS * 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();      // callers launch on non-blocking streams: the zeros must be there
+    if (dev != cur) cudaSetDevice(cur);
     if (e != cudaSuccess) return (int)e;
   }
   const char* m = getenv("VARGP_TC_PERSIST");
