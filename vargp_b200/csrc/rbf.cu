@@ -55,6 +55,56 @@ scale_rows_kernel(const float* __restrict__ src, int64_t R, int64_t D, int64_t s
   }
 }
 
+// Same contract for D <= 1024 (16 B-aligned rows): the source row is read ONCE for all H hyper samples and all of its 16 B
+// chunks are in flight together -- the kernel above re-reads it per sample and walks a row in D / 128 dependent round trips
+// (7 at D = 784), which made the z-side scaling a 23 us latency chain at the head of the Split-MNIST step.
+constexpr int kScaleChunks = 8;           // 8 x 128 floats per row
+constexpr int kFusedRows = 2;             // rows per warp (16 per CTA: 188 CTAs for the 3000 inducing rows of the Split-MNIST step)
+__global__ void __launch_bounds__(kScaleWarps * 32)
+scale_rows_fused_kernel(const float* __restrict__ src, int64_t R, int64_t D, int64_t src_rs,
+                        const float* __restrict__ theta, int64_t theta_rs, int H,
+                        float* __restrict__ dst, float* __restrict__ norms) {
+  pdl_enter();
+  extern __shared__ __align__(16) float s_isig[];          // [H][D]
+  for (int64_t i = threadIdx.x; i < (int64_t)H * D; i += blockDim.x) {
+    const int64_t hh = i / D, d = i - hh * D;
+    s_isig[i] = expf(-theta[hh * theta_rs + d]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t row0 = ((int64_t)blockIdx.x * kScaleWarps + wid) * kFusedRows;
+#pragma unroll 1
+  for (int rr = 0; rr < kFusedRows; ++rr) {
+    const int64_t r = row0 + rr;
+    if (r >= R) break;
+    const float* sp = src + r * src_rs;
+    float4 v[kScaleChunks];
+#pragma unroll
+    for (int i = 0; i < kScaleChunks; ++i) {
+      const int64_t d = lane * 4 + 128 * i;
+      v[i] = d < D ? *reinterpret_cast<const float4*>(sp + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int hh = 0; hh < H; ++hh) {
+      float* dp = dst + ((int64_t)hh * R + r) * D;
+      const float* sg = s_isig + (int64_t)hh * D;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < kScaleChunks; ++i) {
+        const int64_t d = lane * 4 + 128 * i;
+        if (d < D) {
+          const float4 s = *reinterpret_cast<const float4*>(sg + d);
+          float4 w = v[i];
+          w.x *= s.x; w.y *= s.y; w.z *= s.z; w.w *= s.w;
+          acc = fmaf(w.x, w.x, acc); acc = fmaf(w.y, w.y, acc); acc = fmaf(w.z, w.z, acc); acc = fmaf(w.w, w.w, acc);
+          *reinterpret_cast<float4*>(dp + d) = w;
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) norms[(int64_t)hh * R + r] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kbar <- Kbar * K; rsum[g][i] = sum_j; csum[h][j] += sum_{c,i}            (W = Kbar (.) K)
 // grid (column tiles, row chunks, G).  A block owns `rows_blk` rows x (256 * VEC) columns; a thread keeps VEC
@@ -436,6 +486,14 @@ extern "C" int vargp_scale_rows(const float* src, int64_t R, int64_t D, int64_t 
   if (!src || !theta || !dst || !norms || R < 0 || D < 1 || H < 1) return VARGP_ERR_ARG;
   if (R == 0) return 0;
   if (D * sizeof(float) > 48 * 1024) return VARGP_ERR_UNSUPPORTED;
+  const bool vec4 = (D % 4 == 0) && (src_rs % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0);
+  if (vec4 && D <= 128 * kScaleChunks && (size_t)H * D * sizeof(float) <= 48 * 1024) {
+    dim3 fgrid((unsigned)ceil_div(R, kScaleWarps * kFusedRows), 1u);
+    launch_k(scale_rows_fused_kernel, dim3(fgrid), dim3(kScaleWarps * 32), (size_t)H * D * sizeof(float), (cudaStream_t)stream,
+             src, R, D, src_rs, theta, theta_rs, (int)H, dst, norms);
+    return launch_status();
+  }
   dim3 grid((unsigned)ceil_div(R, kScaleWarps * kScaleRowsPerWarp), (unsigned)H);
   launch_k(scale_rows_kernel, dim3(grid), dim3(kScaleWarps * 32), D * sizeof(float), (cudaStream_t)stream, 
       src, R, D, src_rs, theta, theta_rs, dst, norms);
